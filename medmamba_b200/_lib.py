@@ -1,0 +1,86 @@
+"""ctypes loader of the in-tree CUDA library (libmedmamba_b200.so).
+
+There is no fallback: if the shared object is missing and cannot be built, or a call returns a
+non-zero status, this raises.  PyTorch is only the owner of device memory and streams here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+MMB_F32, MMB_BF16, MMB_F16 = 0, 1, 2
+_DTYPES = {torch.float32: MMB_F32, torch.bfloat16: MMB_BF16, torch.float16: MMB_F16}
+ABI_VERSION = 1
+
+_lock = threading.Lock()
+_lib = None
+
+
+class MedMambaLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library (built on first use if the in-tree .so is absent or stale)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = _build.LIB_PATH
+                if not _build.up_to_date():
+                    try:
+                        path = _build.build()
+                    except Exception as e:  # no silent fallback: the product path needs the extension
+                        if not os.path.exists(path):
+                            raise MedMambaLibraryError(
+                                f"libmedmamba_b200.so is missing and could not be built: {e}") from e
+                handle = ctypes.CDLL(path)
+                handle.mmb_status_string.restype = ctypes.c_char_p
+                if handle.mmb_abi_version() != ABI_VERSION:
+                    raise MedMambaLibraryError("libmedmamba_b200.so has a different ABI version; rebuild it")
+                _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().mmb_status_string(ctypes.c_int(status)).decode()
+        raise MedMambaLibraryError(f"{what} failed with status {status}: {msg}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected float32, bfloat16 or float16") from None
+
+
+def ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def i64(v) -> ctypes.c_int64:
+    return ctypes.c_int64(int(v))
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("medmamba_b200 kernels run on CUDA tensors only (there is no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must be on the same CUDA device")
+    return dev

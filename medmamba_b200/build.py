@@ -1,0 +1,84 @@
+"""Builds libmedmamba_b200.so in-tree with nvcc for sm_100a (no torch headers: seconds to build).
+
+The shared object lands next to this file; it is git-ignored (``*.so``) but travels to the GPU
+box with the repo snapshot.  ``python -m medmamba_b200.build [--force] [--verbose]``.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+LIB_PATH = os.path.join(HERE, "libmedmamba_b200.so")
+STAMP = LIB_PATH + ".stamp"
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    files.append(os.path.join(INCLUDE, "medmamba_b200.h"))
+    for f in files:
+        h.update(f.encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def up_to_date() -> bool:
+    return (os.path.exists(LIB_PATH) and os.path.exists(STAMP)
+            and open(STAMP).read().strip() == _digest())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return LIB_PATH
+    objs = []
+    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(HERE, "_build", os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-I", INCLUDE, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        log.append(f"== {os.path.basename(src)}\n{out}")
+        if pr.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    subprocess.check_call(link)
+    with open(os.path.join(HERE, "_build", "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    with open(STAMP, "w") as f:
+        f.write(_digest())
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

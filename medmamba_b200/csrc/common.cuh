@@ -1,0 +1,118 @@
+// Shared device helpers for the SS2D hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/medmamba_b200.h"
+
+namespace mmb {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kMaxState = 16;   // d_state handled per row (MedMamba uses 16 everywhere, MedMamba.py:127)
+
+// One MUFU.EX2 / MUFU.LG2 each, no denormal fix-up code around them.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softplus(x) = log1p(exp(x)), identity above 20 (torch F.softplus defaults; temp.py:63-64).
+// v = e^x; below 1/8 the alternating series (rel. error < 1e-7), above it lg2(1+v) whose
+// absolute error (2^-22) is then small against the result.
+__device__ __forceinline__ float softplus_f(float x) {
+    const float v = ex2_approx(x * kLog2e);
+    const float big = lg2_approx(1.0f + v) * kLn2;
+    float s = fmaf(v, -0.125f, 1.0f / 7.0f);
+    s = fmaf(v, s, -1.0f / 6.0f);
+    s = fmaf(v, s, 0.2f);
+    s = fmaf(v, s, -0.25f);
+    s = fmaf(v, s, 1.0f / 3.0f);
+    s = fmaf(v, s, -0.5f);
+    s = fmaf(v, s, 1.0f);
+    const float r = v < 0.125f ? v * s : big;
+    return x > 20.0f ? x : r;
+}
+
+// d softplus / dx = sigmoid(x) (1 above the threshold, as torch's backward does).
+__device__ __forceinline__ float sigmoid_f(float x) {
+    return rcp_approx(1.0f + ex2_approx(-x * kLog2e));
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// 4 consecutive elements -> float4 (16 B for fp32, 8 B for 16-bit types); p must be aligned to that.
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+template <typename T> __host__ __device__ constexpr int vec4_align() { return 4 * (int)sizeof(T); }
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? MMB_OK : MMB_ERR_CUDA_BASE - (int)e; }
+inline int launch_status() { return cuda_status(cudaGetLastError()); }
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace mmb

@@ -1,0 +1,324 @@
+// selective_scan_fn forward at the interface layout (batch, dim, seqlen) -- the drop-in for
+// mamba_ssm's selective_scan_cuda.fwd reached from MedMamba.py:273-279 (semantics temp.py:57-139).
+//
+// Mapping.  One CTA of 128 threads owns RT = 128/S channel rows of one (batch, group) and walks
+// the sequence in chunks of T steps.  A row is owned by S adjacent lanes; lane q keeps the
+// states n = q, q+S, q+2S, ... in registers for the whole sequence (fp32), so the recurrence
+//     h_n <- exp2(delta * A_n*log2e) * h_n + (delta*u) * B_n ;   y += C_n * h_n
+// costs one MUFU.EX2 and four FMA-pipe ops per (row, step, state) and nothing is re-computed.
+// S is picked on the host so that the launch has enough warps to fill 148 SMs: big batches of
+// wide stages run one thread per row (S = 1), the 96-channel stage-1 shape splits the 16 states
+// over 4 lanes.  The partial y of the S lanes are combined with xor-shuffles.
+//
+// Staging.  Per chunk the CTA loads the u and delta tiles (RT x T, coalesced 128-bit loads along
+// L; delta gets + bias and softplus here, once per element) and the B / C tiles (16 x T, any
+// element strides: the reference passes views with stride(-1) = dt_rank + 2*d_state) into
+// shared memory with a row pitch of T+4 floats, which makes the per-thread LDS.128 reads of
+// four consecutive steps bank-conflict free.  y overwrites u in place and is stored back
+// coalesced (with the optional silu(z) gate) while the next chunk is loaded.
+#include "common.cuh"
+
+namespace mmb {
+
+struct ScanFwdParams {
+    const void* u; const void* delta; const void* Bm; const void* Cm; const void* z; void* out;
+    const float* A; const float* Dv; const float* bias; float* last_state; float* chunk_state;
+    int batch, dim, L, N, G, H, nchunks, softplus;
+    int64_t u_bs, u_ds, d_bs, d_ds, z_bs, z_ds, o_bs, o_ds;
+    int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
+};
+
+template <typename T>
+__device__ __forceinline__ float4 load_row4(const T* row, int t, int len, bool vec) {
+    // 4 consecutive steps t..t+3 of one row, zero beyond len
+    if (vec && t + 4 <= len) return load4<T>(row + t);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t + 0 < len) v.x = to_f<T>(row[t + 0]);
+    if (t + 1 < len) v.y = to_f<T>(row[t + 1]);
+    if (t + 2 < len) v.z = to_f<T>(row[t + 2]);
+    if (t + 3 < len) v.w = to_f<T>(row[t + 3]);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row4(T* row, int t, int len, bool vec, float4 v) {
+    if (vec && t + 4 <= len) { store4<T>(row + t, v); return; }
+    if (t + 0 < len) row[t + 0] = from_f<T>(v.x);
+    if (t + 1 < len) row[t + 1] = from_f<T>(v.y);
+    if (t + 2 < len) row[t + 2] = from_f<T>(v.z);
+    if (t + 3 < len) row[t + 3] = from_f<T>(v.w);
+}
+
+template <int S, int T, typename io_t, typename bc_t>
+__global__ void __launch_bounds__(128) scan_fwd_kernel(const ScanFwdParams p) {
+    constexpr int NT = 128;
+    constexpr int RT = NT / S;           // rows per CTA
+    constexpr int NS = kMaxState / S;    // states per lane
+    constexpr int JB = NS < 8 ? NS : 8;  // states per register block
+    constexpr int TP = T + 4;            // smem row pitch (floats)
+    constexpr int T4 = T / 4;
+
+    extern __shared__ __align__(16) float smem[];
+    float* su = smem;                    // [RT][TP]  u, then y in place
+    float* sd = su + RT * TP;            // [RT][TP]  softplus(delta + bias)
+    float* sB = sd + RT * TP;            // [16][TP]
+    float* sC = sB + kMaxState * TP;     // [16][TP]
+
+    const int tid = threadIdx.x;
+    const int r = tid / S, q = tid % S;
+    const int b = blockIdx.z, g = blockIdx.y;
+    const int row0 = blockIdx.x * RT;                 // first row of the tile inside the group
+    const int rows_here = min(RT, p.H - row0);
+    const bool valid = r < rows_here;
+    const int d = g * p.H + row0 + (valid ? r : 0);   // channel row of this thread
+
+    const io_t* ub = reinterpret_cast<const io_t*>(p.u) + (int64_t)b * p.u_bs;
+    const io_t* db = reinterpret_cast<const io_t*>(p.delta) + (int64_t)b * p.d_bs;
+    const io_t* zb = p.z ? reinterpret_cast<const io_t*>(p.z) + (int64_t)b * p.z_bs : nullptr;
+    io_t* ob = reinterpret_cast<io_t*>(p.out) + (int64_t)b * p.o_bs;
+    const bc_t* Bb = reinterpret_cast<const bc_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
+    const bc_t* Cb = reinterpret_cast<const bc_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+
+    constexpr int VA = vec4_align<io_t>();
+    const bool vec_u = ((reinterpret_cast<uintptr_t>(ub) % VA) == 0) && (p.u_ds % 4 == 0);
+    const bool vec_d = ((reinterpret_cast<uintptr_t>(db) % VA) == 0) && (p.d_ds % 4 == 0);
+    const bool vec_z = zb && ((reinterpret_cast<uintptr_t>(zb) % VA) == 0) && (p.z_ds % 4 == 0);
+    const bool vec_o = ((reinterpret_cast<uintptr_t>(ob) % VA) == 0) && (p.o_ds % 4 == 0);
+
+    float Ap[NS], h[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int n = q + S * j;
+        Ap[j] = (valid && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+        h[j] = 0.f;
+    }
+    const float Dd = (valid && p.Dv) ? p.Dv[d] : 0.f;
+
+    for (int c = 0; c < p.nchunks; ++c) {
+        const int t0 = c * T;
+        const int len = min(T, p.L - t0);
+        // ---- stage: store y of the previous chunk, then load u / delta of this one -----------
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            float4* us = reinterpret_cast<float4*>(su + rr * TP + tt);
+            float4* ds = reinterpret_cast<float4*>(sd + rr * TP + tt);
+            if (rr < rows_here) {
+                const int64_t dd = g * p.H + row0 + rr;
+                if (c > 0) {
+                    float4 y = *us;
+                    const int tp = t0 - T;   // previous chunk is always full
+                    if (zb) {
+                        const float4 zz = load_row4<io_t>(zb + dd * p.z_ds + tp, tt, T, vec_z);
+                        y.x *= silu_f(zz.x); y.y *= silu_f(zz.y); y.z *= silu_f(zz.z); y.w *= silu_f(zz.w);
+                    }
+                    store_row4<io_t>(ob + dd * p.o_ds + tp, tt, T, vec_o, y);
+                }
+                *us = load_row4<io_t>(ub + dd * p.u_ds + t0, tt, len, vec_u);
+                float4 dv = load_row4<io_t>(db + dd * p.d_ds + t0, tt, len, vec_d);
+                const float bs = p.bias ? p.bias[dd] : 0.f;
+                dv.x += bs; dv.y += bs; dv.z += bs; dv.w += bs;
+                if (p.softplus) {
+                    dv.x = softplus_f(dv.x); dv.y = softplus_f(dv.y);
+                    dv.z = softplus_f(dv.z); dv.w = softplus_f(dv.w);
+                }
+                // steps beyond the sequence: delta = 0, u = 0  =>  a = 1, b = 0, state untouched
+                if (tt + 0 >= len) dv.x = 0.f;
+                if (tt + 1 >= len) dv.y = 0.f;
+                if (tt + 2 >= len) dv.z = 0.f;
+                if (tt + 3 >= len) dv.w = 0.f;
+                *ds = dv;
+            } else {
+                *us = make_float4(0.f, 0.f, 0.f, 0.f);
+                *ds = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        // B / C tiles -> [n][TP]; iterate with the unit-stride index fastest
+        if (p.B_ls == 1 || p.B_ns != 1) {
+            for (int idx = tid; idx < kMaxState * T; idx += NT) {
+                const int n = idx / T, tt = idx % T;
+                sB[n * TP + tt] = (n < p.N && tt < len) ? to_f<bc_t>(Bb[(int64_t)n * p.B_ns + (int64_t)(t0 + tt) * p.B_ls]) : 0.f;
+            }
+        } else {
+            for (int idx = tid; idx < kMaxState * T; idx += NT) {
+                const int n = idx % kMaxState, tt = idx / kMaxState;
+                sB[n * TP + tt] = (n < p.N && tt < len) ? to_f<bc_t>(Bb[(int64_t)n + (int64_t)(t0 + tt) * p.B_ls]) : 0.f;
+            }
+        }
+        if (p.C_ls == 1 || p.C_ns != 1) {
+            for (int idx = tid; idx < kMaxState * T; idx += NT) {
+                const int n = idx / T, tt = idx % T;
+                sC[n * TP + tt] = (n < p.N && tt < len) ? to_f<bc_t>(Cb[(int64_t)n * p.C_ns + (int64_t)(t0 + tt) * p.C_ls]) : 0.f;
+            }
+        } else {
+            for (int idx = tid; idx < kMaxState * T; idx += NT) {
+                const int n = idx % kMaxState, tt = idx / kMaxState;
+                sC[n * TP + tt] = (n < p.N && tt < len) ? to_f<bc_t>(Cb[(int64_t)n + (int64_t)(t0 + tt) * p.C_ls]) : 0.f;
+            }
+        }
+        __syncthreads();
+
+        // ---- recurrence over the chunk, four steps per iteration --------------------------------
+        const int steps = (len + 3) & ~3;
+        for (int tt = 0; tt < steps; tt += 4) {
+            const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + tt);
+            const float4 d4 = *reinterpret_cast<const float4*>(sd + r * TP + tt);
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+            float du[4], y[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { du[s] = dl[s] * uu[s]; y[s] = 0.f; }
+#pragma unroll
+            for (int jb = 0; jb < NS; jb += JB) {
+                float4 Bv[JB], Cv[JB];
+#pragma unroll
+                for (int j = 0; j < JB; ++j) {
+                    const int n = q + S * (jb + j);
+                    Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
+                    Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int j = 0; j < JB; ++j) {
+                        const float bb = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
+                        const float cc = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
+                        const float a = ex2_approx(dl[s] * Ap[jb + j]);
+                        h[jb + j] = fmaf(a, h[jb + j], du[s] * bb);
+                        y[s] = fmaf(h[jb + j], cc, y[s]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = S / 2; off > 0; off >>= 1) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) y[s] += __shfl_xor_sync(0xffffffffu, y[s], off);
+            }
+            if (q == 0) {
+                float4 yo;
+                yo.x = fmaf(Dd, uu[0], y[0]); yo.y = fmaf(Dd, uu[1], y[1]);
+                yo.z = fmaf(Dd, uu[2], y[2]); yo.w = fmaf(Dd, uu[3], y[3]);
+                *reinterpret_cast<float4*>(su + r * TP + tt) = yo;
+            }
+        }
+        if (p.chunk_state && valid) {
+            float* cs = p.chunk_state + (((int64_t)b * p.dim + d) * p.nchunks + c) * p.N;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) cs[n] = h[j]; }
+        }
+        __syncthreads();
+    }
+    // ---- tail: y of the last chunk -----------------------------------------------------------
+    {
+        const int t0 = (p.nchunks - 1) * T;
+        const int len = p.L - t0;
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            if (rr < rows_here && tt < len) {
+                const int64_t dd = g * p.H + row0 + rr;
+                float4 y = *reinterpret_cast<const float4*>(su + rr * TP + tt);
+                if (zb) {
+                    const float4 zz = load_row4<io_t>(zb + dd * p.z_ds + t0, tt, len, vec_z);
+                    y.x *= silu_f(zz.x); y.y *= silu_f(zz.y); y.z *= silu_f(zz.z); y.w *= silu_f(zz.w);
+                }
+                store_row4<io_t>(ob + dd * p.o_ds + t0, tt, len, vec_o, y);
+            }
+        }
+    }
+    if (p.last_state && valid) {
+        float* ls = p.last_state + ((int64_t)b * p.dim + d) * p.N;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) ls[n] = h[j]; }
+    }
+}
+
+template <int S, int T> constexpr size_t scan_fwd_smem() {
+    return sizeof(float) * (size_t)(2 * (128 / S) + 2 * kMaxState) * (T + 4);
+}
+
+// lanes per row: the smallest split that gives the launch ~2 waves of 16 warps per SM
+static int pick_split(int batch, int dim) {
+    const long rows = (long)batch * dim;
+    const long want_threads = 32L * 16 * num_sms();
+    int S = 1;
+    while (S < 16 && rows * S < want_threads) S *= 2;
+    return S;
+}
+static int chunk_for_split(int S) { return S == 1 ? 32 : 64; }
+
+template <int S, int T, typename io_t, typename bc_t>
+static int launch_scan_fwd(const ScanFwdParams& p, cudaStream_t stream) {
+    constexpr size_t smem = scan_fwd_smem<S, T>();
+    auto kern = scan_fwd_kernel<S, T, io_t, bc_t>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    const int RT = 128 / S;
+    dim3 grid((p.H + RT - 1) / RT, p.G, p.batch);
+    kern<<<grid, 128, smem, stream>>>(p);
+    return launch_status();
+}
+
+template <typename io_t, typename bc_t>
+static int dispatch_split(const ScanFwdParams& p, int S, cudaStream_t stream) {
+    switch (S) {
+        case 1: return launch_scan_fwd<1, 32, io_t, bc_t>(p, stream);
+        case 2: return launch_scan_fwd<2, 64, io_t, bc_t>(p, stream);
+        case 4: return launch_scan_fwd<4, 64, io_t, bc_t>(p, stream);
+        case 8: return launch_scan_fwd<8, 64, io_t, bc_t>(p, stream);
+        default: return launch_scan_fwd<16, 64, io_t, bc_t>(p, stream);
+    }
+}
+
+template <typename io_t>
+static int dispatch_bc(const ScanFwdParams& p, int io_dtype, int bc_dtype, int S, cudaStream_t stream) {
+    // B / C come either in the dtype of u (what mamba_ssm does) or in fp32 (what MedMamba passes)
+    if (bc_dtype == MMB_F32) return dispatch_split<io_t, float>(p, S, stream);
+    if (bc_dtype == io_dtype) return dispatch_split<io_t, io_t>(p, S, stream);
+    return MMB_ERR_UNSUPPORTED;
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_scan_chunk_len(int batch, int dim, int seqlen) {
+    (void)seqlen;
+    if (batch <= 0 || dim <= 0) return MMB_ERR_INVALID_ARG;
+    return mmb::chunk_for_split(mmb::pick_split(batch, dim));
+}
+
+extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
+                            const float* Dv, const void* z, const float* delta_bias, void* out,
+                            float* last_state, float* chunk_state,
+                            int batch, int dim, int seqlen, int dstate, int ngroups,
+                            int64_t u_bs, int64_t u_ds, int64_t delta_bs, int64_t delta_ds,
+                            int64_t z_bs, int64_t z_ds, int64_t out_bs, int64_t out_ds,
+                            int64_t B_bs, int64_t B_gs, int64_t B_ns, int64_t B_ls,
+                            int64_t C_bs, int64_t C_gs, int64_t C_ns, int64_t C_ls,
+                            int delta_softplus, int io_dtype, int bc_dtype, void* stream) {
+    using namespace mmb;
+    if (!u || !delta || !A || !Bm || !Cm || !out) return MMB_ERR_INVALID_ARG;
+    if (batch < 0 || dim <= 0 || seqlen < 0 || dstate <= 0 || ngroups <= 0) return MMB_ERR_INVALID_ARG;
+    if (dim % ngroups != 0) return MMB_ERR_INVALID_ARG;
+    if (dstate > kMaxState) return MMB_ERR_UNSUPPORTED;
+    if (batch > 65535 || ngroups > 65535) return MMB_ERR_UNSUPPORTED;
+    if (batch == 0 || seqlen == 0) return MMB_OK;
+    ScanFwdParams p;
+    p.u = u; p.delta = delta; p.Bm = Bm; p.Cm = Cm; p.z = z; p.out = out;
+    p.A = A; p.Dv = Dv; p.bias = delta_bias; p.last_state = last_state; p.chunk_state = chunk_state;
+    p.batch = batch; p.dim = dim; p.L = seqlen; p.N = dstate; p.G = ngroups; p.H = dim / ngroups;
+    p.softplus = delta_softplus;
+    p.u_bs = u_bs; p.u_ds = u_ds; p.d_bs = delta_bs; p.d_ds = delta_ds;
+    p.z_bs = z_bs; p.z_ds = z_ds; p.o_bs = out_bs; p.o_ds = out_ds;
+    p.B_bs = B_bs; p.B_gs = B_gs; p.B_ns = B_ns; p.B_ls = B_ls;
+    p.C_bs = C_bs; p.C_gs = C_gs; p.C_ns = C_ns; p.C_ls = C_ls;
+    const int S = pick_split(batch, dim);
+    const int T = chunk_for_split(S);
+    p.nchunks = (seqlen + T - 1) / T;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (io_dtype) {
+        case MMB_F32: return dispatch_bc<float>(p, io_dtype, bc_dtype, S, st);
+        case MMB_BF16: return dispatch_bc<__nv_bfloat16>(p, io_dtype, bc_dtype, S, st);
+        case MMB_F16: return dispatch_bc<__half>(p, io_dtype, bc_dtype, S, st);
+        default: return MMB_ERR_INVALID_ARG;
+    }
+}
