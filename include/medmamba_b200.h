@@ -67,6 +67,55 @@ int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* B
                  int64_t C_bs, int64_t C_gs, int64_t C_ns, int64_t C_ls,
                  int delta_softplus, int io_dtype, int bc_dtype, void* stream);
 
+/* ---- fused SS2D path (channels-last; every tensor is indexed by token position p = h*W + w) ---- */
+
+/* Depthwise 3x3 conv (padding 1) + bias + SiLU on a channels-last view.  Replaces the NHWC->NCHW
+ * copy, cuDNN depthwise conv and SiLU of MedMamba.py:294-295 (conv defined at :153-161).
+ *   x      : (batch, H, W, D) view, channel stride 1, pixel stride x_pixel_stride, batch stride
+ *            x_batch_stride (elements) -- the first half of the in_proj output has pitch 2*D
+ *   weight : (D, 1, 3, 3) fp32 contiguous;  bias: (D) fp32 or NULL
+ *   out    : (batch, H, W, D) dense, dtype out_dtype (MMB_F32)
+ * D % 4 == 0. */
+int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const float* bias, void* out,
+                           int batch, int H, int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride,
+                           int in_dtype, int out_dtype, void* stream);
+
+/* dt_rank padded to the widths the core kernel is instantiated for (host only);
+ * MMB_ERR_UNSUPPORTED when dt_rank > 32. */
+int mmb_ss2d_core_dt_pad(int dt_rank);
+
+/* Four-direction selective scan of SS2D.forward_corev0 in one launch.  Replaces the cross-scan
+ * (MedMamba.py:256-257), the dt_proj einsum and its copy (:262, :266), selective_scan_fn (:273-279,
+ * delta_softplus=True, delta_bias=dt_projs_bias, z=None) and the flips / transposes of the
+ * cross-merge (:282-286).
+ *   xc    : (batch, H, W, D) fp32 dense        -- u of all four directions
+ *   proj  : (batch, H, W, 4, 32 + dt_pad) fp32 -- per direction k the x_proj of the token:
+ *           [0,16) = B_n, [16,32) = C_n (rows n >= dstate zero), [32, 32+dt_rank) = dt_r, rest zero
+ *   Wdt   : (4, D, dt_rank)   dt_bias: (4, D)   A: (4*D, dstate) (= -exp(A_logs))   Ds: (4*D)
+ *   ydir  : (batch, H, W, 4, D) fp32 -- direction k's scan output stored at the token it belongs to
+ * Direction order and index maps: SURVEY.md Appendix A.  D % 4 == 0, dstate <= 16, dt_rank <= 32. */
+int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float* Wdt, const float* dt_bias,
+                      const float* A, const float* Ds, float* ydir,
+                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, void* stream);
+
+/* y = ((y0 + y2) + y1) + y3 over ydir's direction slices (the operand order of MedMamba.py:298),
+ * LayerNorm over D (MedMamba.py:300, eps as given) and * SiLU(z) (MedMamba.py:301).
+ *   ydir : (tokens, 4, D) fp32;  z: (tokens, D) view with pixel stride z_pixel_stride, dtype z_dtype
+ *   out  : (tokens, D) dense, dtype out_dtype (== z_dtype);  ymerged: NULL or (tokens, D) fp32, the
+ *          pre-norm sum (kept for the backward).  D % 4 == 0, D <= 1024. */
+int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const float* gamma, const float* beta,
+                         void* out, float* ymerged, int64_t tokens, int D, int64_t z_pixel_stride,
+                         float eps, int z_dtype, int out_dtype, void* stream);
+
+/* out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
+ * -- torch.cat + channel_shuffle(groups=2) + residual of MedMamba.py:355-357 (:308-320).
+ *   left, ssm : (tokens, c) views, channel stride 1;  inp: (tokens, 2c) view;  out: (tokens, 2c) dense
+ * c % 4 == 0. */
+int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* inp, void* out,
+                                 int64_t tokens, int c, int64_t left_pixel_stride,
+                                 int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int dtype,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

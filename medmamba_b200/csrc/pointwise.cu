@@ -1,0 +1,258 @@
+// The bandwidth-bound kernels either side of the scan, all channels-last (B, H, W, C):
+//   dwconv3x3 + bias + SiLU        replaces MedMamba.py:294-295 (permute copy, cuDNN depthwise conv, SiLU)
+//   (y0+y2+y1+y3) -> LayerNorm -> * SiLU(z)   replaces MedMamba.py:298-301 (3 adds, transpose copy, LN, gate)
+//   cat + channel_shuffle(2) + residual       replaces MedMamba.py:355-357 and :308-320
+// Each reads its inputs once with 128-bit loads and writes its output once.
+#include "common.cuh"
+
+namespace mmb {
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3, padding 1, + bias, SiLU.  x is a channels-last view with an arbitrary pixel pitch
+// (it is the first half of the in_proj output, pitch 2*D); out is dense (B, H, W, D).
+// A thread owns 4 channels and a strip of WS output pixels along w: 3 x (WS + 2) float4 loads.
+template <int WS, typename in_t, typename out_t>
+__global__ void __launch_bounds__(256)
+dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                      out_t* __restrict__ out, int B, int H, int W, int D, int64_t x_pix, int64_t x_batch) {
+    const int C4 = D / 4;
+    const int strips = (W + WS - 1) / WS;
+    const int64_t total = (int64_t)B * H * strips * C4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        int64_t r = idx / C4;
+        const int st = (int)(r % strips); r /= strips;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        const int c = c4 * 4, w0 = st * WS;
+        float wk[9][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) wk[tp][e] = __ldg(wgt + (int64_t)(c + e) * 9 + tp);
+        }
+        float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+        float acc[WS][4];
+#pragma unroll
+        for (int i = 0; i < WS; ++i) { acc[i][0] = bs.x; acc[i][1] = bs.y; acc[i][2] = bs.z; acc[i][3] = bs.w; }
+        const in_t* xb = x + (int64_t)b * x_batch + c;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int hy = h + dy - 1;
+            if (hy < 0 || hy >= H) continue;
+#pragma unroll
+            for (int j = 0; j < WS + 2; ++j) {
+                const int wx = w0 + j - 1;
+                if (wx < 0 || wx >= W) continue;
+                const float4 v = load4<in_t>(xb + ((int64_t)hy * W + wx) * x_pix);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int i = j - dx;          // output pixel this input contributes to with tap (dy, dx)
+                    if (i >= 0 && i < WS) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[i][e] = fmaf(wk[dy * 3 + dx][e], vv[e], acc[i][e]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < WS; ++i) {
+            const int wx = w0 + i;
+            if (wx < W) {
+                float4 o;
+                o.x = silu_f(acc[i][0]); o.y = silu_f(acc[i][1]); o.z = silu_f(acc[i][2]); o.w = silu_f(acc[i][3]);
+                store4<out_t>(out + (((int64_t)b * H + h) * W + wx) * D + c, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp per token: y = ((y0 + y2) + y1) + y3 over the four direction slices of ydir (B, L, 4, D)
+// -- the order of `y1 + y2 + y3 + y4` at MedMamba.py:298, whose operands are out0, flipped out2,
+// transposed out1, flipped-transposed out3 (MedMamba.py:286) -- then LayerNorm over D and * SiLU(z).
+template <int V, typename z_t, typename out_t>   // V float4 per lane: D <= 128 * V
+__global__ void __launch_bounds__(256)
+outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, out_t* __restrict__ out, float* __restrict__ ymerged,
+                    int64_t tokens, int D, int64_t z_pix, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int C4 = D / 4;
+    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+        const float4* y0 = reinterpret_cast<const float4*>(ydir + tok * 4 * D);
+        float4 v[V];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float4 a = __ldg(y0 + c4), bq = __ldg(y0 + C4 + c4), cq = __ldg(y0 + 2 * C4 + c4), dq = __ldg(y0 + 3 * C4 + c4);
+                v[i].x = ((a.x + cq.x) + bq.x) + dq.x; v[i].y = ((a.y + cq.y) + bq.y) + dq.y;
+                v[i].z = ((a.z + cq.z) + bq.z) + dq.z; v[i].w = ((a.w + cq.w) + bq.w) + dq.w;
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                if (ymerged) reinterpret_cast<float4*>(ymerged + tok * D)[c4] = v[i];
+            } else {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (lane + 32 * i < C4) {
+                const float a = v[i].x - mean, bq = v[i].y - mean, cq = v[i].z - mean, dq = v[i].w - mean;
+                sq += (a * a + bq * bq) + (cq * cq + dq * dq);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        const float rstd = rsqrtf(sq / (float)D + eps);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+                const float4 zz = load4<z_t>(z + tok * z_pix + 4 * c4);
+                float4 o;
+                o.x = fmaf((v[i].x - mean) * rstd, g.x, bt.x) * silu_f(zz.x);
+                o.y = fmaf((v[i].y - mean) * rstd, g.y, bt.y) * silu_f(zz.y);
+                o.z = fmaf((v[i].z - mean) * rstd, g.z, bt.z) * silu_f(zz.z);
+                o.w = fmaf((v[i].w - mean) * rstd, g.w, bt.w) * silu_f(zz.w);
+                store4<out_t>(out + tok * D + 4 * c4, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
+// (torch.cat + channel_shuffle(groups=2) + residual).  A thread produces 8 output channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+shuffle_cat_residual_kernel(const T* __restrict__ left, const T* __restrict__ ssm, const T* __restrict__ inp,
+                            T* __restrict__ out, int64_t tokens, int c, int64_t left_pix, int64_t ssm_pix,
+                            int64_t inp_pix) {
+    const int C4 = c / 4;
+    const int64_t total = tokens * C4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        const int64_t tok = idx / C4;
+        const float4 l = load4<T>(left + tok * left_pix + 4 * c4);
+        const float4 s = load4<T>(ssm + tok * ssm_pix + 4 * c4);
+        const float4 i0 = load4<T>(inp + tok * inp_pix + 8 * c4);
+        const float4 i1 = load4<T>(inp + tok * inp_pix + 8 * c4 + 4);
+        float4 o0, o1;
+        o0.x = l.x + i0.x; o0.y = s.x + i0.y; o0.z = l.y + i0.z; o0.w = s.y + i0.w;
+        o1.x = l.z + i1.x; o1.y = s.z + i1.y; o1.z = l.w + i1.z; o1.w = s.w + i1.w;
+        store4<T>(out + tok * 2 * c + 8 * c4, o0);
+        store4<T>(out + tok * 2 * c + 8 * c4 + 4, o1);
+    }
+}
+
+static int grid_for(int64_t work_items, int threads) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T> static bool aligned_for4(const void* p) { return reinterpret_cast<uintptr_t>(p) % vec4_align<T>() == 0; }
+
+}  // namespace mmb
+
+extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const float* bias, void* out,
+                                      int batch, int H, int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride,
+                                      int in_dtype, int out_dtype, void* stream) {
+    using namespace mmb;
+    if (!x || !weight || !out) return MMB_ERR_INVALID_ARG;
+    if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
+    if (D % 4 != 0 || x_pixel_stride % 4 != 0 || x_batch_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if (bias && reinterpret_cast<uintptr_t>(bias) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    if (batch == 0) return MMB_OK;
+    constexpr int WS = 4;
+    const int64_t items = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 4);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(items, 256);
+#define MMB_DW(IN, OUT)                                                                                          \
+    do {                                                                                                         \
+        if (!aligned_for4<IN>(x) || !aligned_for4<OUT>(out)) return MMB_ERR_UNSUPPORTED;                         \
+        dwconv3x3_silu_kernel<WS, IN, OUT><<<grid, 256, 0, st>>>(reinterpret_cast<const IN*>(x), weight, bias,   \
+            reinterpret_cast<OUT*>(out), batch, H, W, D, x_pixel_stride, x_batch_stride);                        \
+        return launch_status();                                                                                  \
+    } while (0)
+    if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_DW(float, float);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_DW(__nv_bfloat16, float);
+    if (in_dtype == MMB_F16 && out_dtype == MMB_F32) MMB_DW(__half, float);
+#undef MMB_DW
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const float* gamma, const float* beta,
+                                    void* out, float* ymerged, int64_t tokens, int D, int64_t z_pixel_stride,
+                                    float eps, int z_dtype, int out_dtype, void* stream) {
+    using namespace mmb;
+    if (!ydir || !z || !gamma || !beta || !out) return MMB_ERR_INVALID_ARG;
+    if (tokens < 0 || D <= 0) return MMB_ERR_INVALID_ARG;
+    if (D % 4 != 0 || D > 1024 || z_pixel_stride % 4 != 0 || z_dtype != out_dtype) return MMB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(ydir) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+         reinterpret_cast<uintptr_t>(ymerged)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    if (tokens == 0) return MMB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(tokens * 32, 256);
+#define MMB_ON(V, T)                                                                                             \
+    do {                                                                                                         \
+        if (!aligned_for4<T>(z) || !aligned_for4<T>(out)) return MMB_ERR_UNSUPPORTED;                            \
+        outnorm_gate_kernel<V, T, T><<<grid, 256, 0, st>>>(ydir, reinterpret_cast<const T*>(z), gamma, beta,     \
+            reinterpret_cast<T*>(out), ymerged, tokens, D, z_pixel_stride, eps);                                 \
+        return launch_status();                                                                                  \
+    } while (0)
+#define MMB_ON_V(T)                                                                                              \
+    do {                                                                                                         \
+        if (D <= 128) MMB_ON(1, T);                                                                              \
+        if (D <= 256) MMB_ON(2, T);                                                                              \
+        if (D <= 512) MMB_ON(4, T);                                                                              \
+        MMB_ON(8, T);                                                                                            \
+    } while (0)
+    if (z_dtype == MMB_F32) MMB_ON_V(float);
+    if (z_dtype == MMB_BF16) MMB_ON_V(__nv_bfloat16);
+    if (z_dtype == MMB_F16) MMB_ON_V(__half);
+#undef MMB_ON_V
+#undef MMB_ON
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* inp, void* out,
+                                            int64_t tokens, int c, int64_t left_pixel_stride,
+                                            int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int dtype,
+                                            void* stream) {
+    using namespace mmb;
+    if (!left || !ssm || !inp || !out) return MMB_ERR_INVALID_ARG;
+    if (tokens < 0 || c <= 0) return MMB_ERR_INVALID_ARG;
+    if (c % 4 != 0 || left_pixel_stride % 4 != 0 || ssm_pixel_stride % 4 != 0 || inp_pixel_stride % 4 != 0)
+        return MMB_ERR_UNSUPPORTED;
+    if (tokens == 0) return MMB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(tokens * (c / 4), 256);
+#define MMB_SH(T)                                                                                                \
+    do {                                                                                                         \
+        if (!aligned_for4<T>(left) || !aligned_for4<T>(ssm) || !aligned_for4<T>(inp) || !aligned_for4<T>(out))   \
+            return MMB_ERR_UNSUPPORTED;                                                                          \
+        shuffle_cat_residual_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(left),                   \
+            reinterpret_cast<const T*>(ssm), reinterpret_cast<const T*>(inp), reinterpret_cast<T*>(out), tokens, \
+            c, left_pixel_stride, ssm_pixel_stride, inp_pixel_stride);                                           \
+        return launch_status();                                                                                  \
+    } while (0)
+    if (dtype == MMB_F32) MMB_SH(float);
+    if (dtype == MMB_BF16) MMB_SH(__nv_bfloat16);
+    if (dtype == MMB_F16) MMB_SH(__half);
+#undef MMB_SH
+    return MMB_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,328 @@
+// Fused SS2D core, forward: cross-scan + dt_proj + softplus + selective scan + cross-merge addressing.
+// Replaces MedMamba.py:256-257 (cross-scan), :262,:266 (dt_proj einsum + copy), :273-279
+// (selective_scan_fn) and :282-286 (flip / transpose back) for all four directions in one launch.
+//
+// Layout (channels-last, everything indexed by the token position p = h*W + w, never by the
+// per-direction sequence index):
+//   xc   (B, H, W, D)        conv+SiLU output = u for every direction             [fp32]
+//   proj (B, H, W, 4, CP)    x_proj of the un-permuted tokens, per direction k:
+//                            [ B_n (16) | C_n (16) | dt_r (RP, zero padded) ]      [fp32]
+//   ydir (B, H, W, 4, D)     scan output of direction k written at the position it belongs to;
+//                            the out_norm kernel adds the four in the reference's order.
+// Direction k walks the positions in the order of SURVEY.md Appendix A (row-major, column-major
+// and their reverses), so no flipped or transposed copy of anything is ever materialised.
+//
+// One CTA owns (batch b, direction k, CT channels) for the whole sequence: a producer warp streams
+// blocks of consecutive steps of xc and proj into a shared-memory ring with TMA tensor copies
+// (a row block for k = 0, 2; a column block for k = 1, 3) signalled through mbarriers; the
+// consumer warps hold one channel per S lanes with the 16/S states of the lane in registers.
+// Per step and state: one MUFU.EX2 and four FMA-pipe operations; the kernel is bound by the
+// 16 exp/clk/SM MUFU rate, not by HBM.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace mmb {
+
+constexpr int kCoreStages = 4;
+constexpr int kCoreStageBytes = 24 * 1024;
+
+struct CoreFwdParams {
+    float* ydir;
+    const float* Wdt;     // (4, D, R)
+    const float* bias;    // (4, D)
+    const float* A;       // (4*D, N)
+    const float* Ds;      // (4*D)
+    int B, H, W, L, D, N, R, CT;
+    int T_row, NB_row;                 // row view: NB_row blocks of T_row consecutive positions
+    int nw, T_col, NI_col, NO_col;     // column view: NO_col column groups x NI_col row blocks
+    int cap;                           // steps a stage can hold
+};
+
+template <int S, int RP>
+__global__ void __launch_bounds__(416)
+ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
+                     const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
+                     const CoreFwdParams p) {
+    constexpr int NS = kMaxState / S;
+    constexpr int CP = 32 + RP;
+    constexpr int OWN = 4 / S;          // delta evaluations per lane per group of 4 steps
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int xbytes = p.cap * p.CT * 4, pbytes = p.cap * CP * 4;
+    const int xpad = (xbytes + 127) & ~127, ppad = (pbytes + 127) & ~127;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kCoreStages * (xpad + ppad));
+    uint64_t* empty = full + kCoreStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncons = (blockDim.x >> 5) - 1;
+    const int k = blockIdx.y, b = blockIdx.z, c0 = blockIdx.x * p.CT;
+    const bool colview = (k & 1) != 0, rev = k >= 2;
+    const int NB = colview ? p.NO_col * p.NI_col : p.NB_row;
+
+    if (tid == 0) {
+        for (int s = 0; s < kCoreStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncons); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == ncons) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            prefetch_tmap(colview ? &tmx_col : &tmx_row);
+            prefetch_tmap(colview ? &tmp_col : &tmp_row);
+            for (int j = 0; j < NB; ++j) {
+                const int s = j % kCoreStages, ph = (j / kCoreStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int blk = rev ? NB - 1 - j : j;
+                uint8_t* xs = smem_raw + s * (xpad + ppad);
+                uint8_t* ps = xs + xpad;
+                if (!colview) {
+                    mbar_expect_tx(&full[s], p.T_row * (p.CT + CP) * 4);
+                    tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
+                    tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
+                } else {
+                    const int o = blk / p.NI_col, i = blk % p.NI_col;
+                    mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT + CP) * 4);
+                    tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
+                    tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int t = warp * 32 + lane;
+    const int cl = t / S, q = t % S;            // channel inside the tile, state split index
+    const int c = c0 + cl;
+    const bool cvalid = c < p.D;
+    const int row = k * p.D + (cvalid ? c : 0);
+    const int lane_base = lane & ~(S - 1);
+
+    float Ap[NS], h[NS], Wd[RP];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int n = (j & 3) + 4 * q + 4 * S * (j >> 2);
+        Ap[j] = (cvalid && n < p.N) ? p.A[(int64_t)row * p.N + n] * kLog2e : 0.f;
+        h[j] = 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r) Wd[r] = (cvalid && r < p.R) ? p.Wdt[(int64_t)row * p.R + r] : 0.f;
+    const float bias = cvalid ? p.bias[row] : 0.f;
+    const float Dd = cvalid ? p.Ds[row] : 0.f;
+    float* yb = p.ydir + ((int64_t)b * p.L * 4 + k) * p.D + c;   // + pos * 4 * D
+
+    for (int jb = 0; jb < NB; ++jb) {
+        const int s = jb % kCoreStages, ph = (jb / kCoreStages) & 1;
+        const int blk = rev ? NB - 1 - jb : jb;
+        // geometry of the block: nrows x ncols positions, slot = hh*nwbox + ww, pos = pbase + hh*psh + ww
+        int nrows, ncols, nwbox, psh, pbase;
+        if (!colview) {
+            pbase = blk * p.T_row; nrows = min(p.T_row, p.L - pbase); ncols = 1; nwbox = 1; psh = 1;
+        } else {
+            const int o = blk / p.NI_col, i = blk % p.NI_col;
+            const int w0 = o * p.nw, h0 = i * p.T_col;
+            nrows = min(p.T_col, p.H - h0); ncols = min(p.nw, p.W - w0); nwbox = p.nw; psh = p.W;
+            pbase = h0 * p.W + w0;
+        }
+        const int nsteps = nrows * ncols;
+        const float* xs = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad));
+        const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
+        mbar_wait(&full[s], ph);
+
+        int ww = rev ? ncols - 1 : 0, hh = rev ? nrows - 1 : 0;   // position of the next step in time order
+        for (int g0 = 0; g0 < nsteps; g0 += 4) {
+            int slot[4], pos[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ok[i] = g0 + i < nsteps;
+                slot[i] = ok[i] ? hh * nwbox + ww : 0;
+                pos[i] = pbase + hh * psh + ww;
+                if (!rev) { if (++hh == nrows) { hh = 0; ++ww; } }
+                else      { if (--hh < 0) { hh = nrows - 1; --ww; } }
+            }
+            // u of the four steps (all S lanes of a channel read the same word)
+            float uu[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? xs[slot[i] * p.CT + cl] : 0.f;
+            // delta = softplus(Wdt . dt_r + bias): each lane evaluates OWN of the four steps
+            float down[OWN];
+#pragma unroll
+            for (int m = 0; m < OWN; ++m) {
+                const int i = q + S * m;            // step handled by this lane
+                // slot[i] with a lane-dependent i: select without dynamic register indexing
+                int sl = slot[0]; bool okk = ok[0];
+#pragma unroll
+                for (int ii = 1; ii < 4; ++ii) if (ii == i) { sl = slot[ii]; okk = ok[ii]; }
+                const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
+                float acc0 = bias, acc1 = 0.f;
+#pragma unroll
+                for (int r4 = 0; r4 < RP / 4; ++r4) {
+                    const float4 v = dtp[r4];
+                    acc0 = fmaf(Wd[4 * r4 + 0], v.x, acc0); acc1 = fmaf(Wd[4 * r4 + 1], v.y, acc1);
+                    acc0 = fmaf(Wd[4 * r4 + 2], v.z, acc0); acc1 = fmaf(Wd[4 * r4 + 3], v.w, acc1);
+                }
+                down[m] = okk ? softplus_f(acc0 + acc1) : 0.f;
+            }
+            float dl[4], du[4], y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dl[i] = S == 1 ? down[i] : __shfl_sync(0xffffffffu, down[i / S], lane_base + (i % S));
+                du[i] = dl[i] * uu[i];
+                y[i] = 0.f;
+            }
+            // recurrence
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4* bp = reinterpret_cast<const float4*>(ps + slot[i] * CP) + q;
+                const float4* cp = bp + 4;
+#pragma unroll
+                for (int j4 = 0; j4 < NS / 4; ++j4) {
+                    const float4 bv = bp[j4 * S], cv = cp[j4 * S];
+                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = j4 * 4 + e;
+                        const float a = ex2_approx(dl[i] * Ap[j]);
+                        h[j] = fmaf(a, h[j], du[i] * bb[e]);
+                        y[i] = fmaf(h[j], cc[e], y[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = S / 2; off > 0; off >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] += __shfl_xor_sync(0xffffffffu, y[i], off);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (ok[i] && cvalid && q == (i % S)) yb[(int64_t)pos[i] * 4 * p.D] = fmaf(Dd, uu[i], y[i]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+}
+
+struct CorePlan {
+    int S, CT, tiles, T_row, NB_row, nw, T_col, NI_col, NO_col, cap, threads;
+    size_t smem;
+};
+
+static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
+    const long rows = 4L * B * D;
+    const long want = 32L * 16 * num_sms();
+    int S = 1;
+    while (S < 4 && rows * S < want) S *= 2;
+    const int gran = 32 / S;                          // channels per warp
+    int capc = 256 < 384 / S ? 256 : 384 / S;
+    capc -= capc % gran;
+    int tiles = (D + capc - 1) / capc;
+    int CT = (D + tiles - 1) / tiles;
+    CT = (CT + gran - 1) / gran * gran;
+    tiles = (D + CT - 1) / CT;
+    const int CP = 32 + RP;
+    int cap = kCoreStageBytes / ((CT + CP) * 4);
+    if (cap > 32) cap = 32;
+    if (cap < 4) return false;
+    const int L = H * W;
+    pl.NB_row = (L + cap - 1) / cap;
+    pl.T_row = (L + pl.NB_row - 1) / pl.NB_row;
+    if (H <= cap) {
+        const int maxw = cap / H;
+        pl.NO_col = (W + maxw - 1) / maxw;
+        pl.nw = (W + pl.NO_col - 1) / pl.NO_col;
+        pl.T_col = H; pl.NI_col = 1;
+    } else {
+        pl.nw = 1; pl.NO_col = W;
+        pl.NI_col = (H + cap - 1) / cap;
+        pl.T_col = (H + pl.NI_col - 1) / pl.NI_col;
+    }
+    if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256 || CT > 256) return false;
+    pl.cap = pl.T_row > pl.nw * pl.T_col ? pl.T_row : pl.nw * pl.T_col;
+    pl.S = S; pl.CT = CT; pl.tiles = tiles;
+    pl.threads = (CT * S / 32 + 1) * 32;
+    const size_t xpad = ((size_t)pl.cap * CT * 4 + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
+    pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
+    return true;
+}
+
+template <int S, int RP>
+static int launch_core(const CorePlan& pl, const CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+    constexpr int CP = 32 + RP;
+    CUtensorMap tmx_row, tmx_col, tmp_row, tmp_col;
+    const uint64_t B = p.B, H = p.H, W = p.W, L = p.L, D = p.D;
+    {
+        const uint64_t dims[3] = {D, L, B}, str[2] = {D * 4, L * D * 4};
+        const uint32_t box[3] = {(uint32_t)pl.CT, (uint32_t)pl.T_row, 1};
+        if (!make_tmap(&tmx_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+    }
+    {
+        const uint64_t dims[4] = {D, W, H, B}, str[3] = {D * 4, W * D * 4, L * D * 4};
+        const uint32_t box[4] = {(uint32_t)pl.CT, (uint32_t)pl.nw, (uint32_t)pl.T_col, 1};
+        if (!make_tmap(&tmx_col, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+    }
+    {
+        const uint64_t dims[4] = {CP, 4, L, B}, str[3] = {CP * 4, 4 * CP * 4, L * 4 * CP * 4};
+        const uint32_t box[4] = {CP, 1, (uint32_t)pl.T_row, 1};
+        if (!make_tmap(&tmp_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, proj, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+    }
+    {
+        const uint64_t dims[5] = {CP, 4, W, H, B}, str[4] = {CP * 4, 4 * CP * 4, W * 4 * CP * 4, L * 4 * CP * 4};
+        const uint32_t box[5] = {CP, 1, (uint32_t)pl.nw, (uint32_t)pl.T_col, 1};
+        if (!make_tmap(&tmp_col, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, proj, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+    }
+    auto kern = ss2d_core_fwd_kernel<S, RP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    dim3 grid(pl.tiles, 4, p.B);
+    kern<<<grid, pl.threads, pl.smem, st>>>(tmx_row, tmx_col, tmp_row, tmp_col, p);
+    return launch_status();
+}
+
+template <int RP>
+static int dispatch_core_s(const CorePlan& pl, const CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+    switch (pl.S) {
+        case 1: return launch_core<1, RP>(pl, p, xc, proj, st);
+        case 2: return launch_core<2, RP>(pl, p, xc, proj, st);
+        default: return launch_core<4, RP>(pl, p, xc, proj, st);
+    }
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_ss2d_core_dt_pad(int dt_rank) {
+    const int sup[6] = {4, 8, 12, 16, 24, 32};
+    for (int i = 0; i < 6; ++i) if (dt_rank <= sup[i]) return sup[i];
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float* Wdt, const float* dt_bias,
+                                 const float* A, const float* Ds, float* ydir,
+                                 int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, void* stream) {
+    using namespace mmb;
+    if (!xc || !proj || !Wdt || !dt_bias || !A || !Ds || !ydir) return MMB_ERR_INVALID_ARG;
+    if (batch < 0 || H <= 0 || W <= 0 || D <= 0 || dstate <= 0 || dt_rank <= 0) return MMB_ERR_INVALID_ARG;
+    if (dstate > kMaxState || dt_pad != mmb_ss2d_core_dt_pad(dt_rank)) return MMB_ERR_UNSUPPORTED;
+    if (D % 4 != 0 || batch > 65535) return MMB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(xc) | reinterpret_cast<uintptr_t>(proj)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    if (batch == 0) return MMB_OK;
+    CorePlan pl;
+    if (!plan_core(batch, H, W, D, dt_pad, pl)) return MMB_ERR_UNSUPPORTED;
+    CoreFwdParams p;
+    p.ydir = ydir; p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds;
+    p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank; p.CT = pl.CT;
+    p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
+    p.cap = pl.cap;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (dt_pad) {
+        case 4: return dispatch_core_s<4>(pl, p, xc, proj, st);
+        case 8: return dispatch_core_s<8>(pl, p, xc, proj, st);
+        case 12: return dispatch_core_s<12>(pl, p, xc, proj, st);
+        case 16: return dispatch_core_s<16>(pl, p, xc, proj, st);
+        case 24: return dispatch_core_s<24>(pl, p, xc, proj, st);
+        case 32: return dispatch_core_s<32>(pl, p, xc, proj, st);
+        default: return MMB_ERR_UNSUPPORTED;
+    }
+}

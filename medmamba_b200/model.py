@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference's module API around the SS2D hot path.
+
+Same class names, constructor arguments, parameter names / shapes and ``state_dict`` keys as
+``MedMamba.py`` (``SS2D`` :123-191, ``SS_Conv_SSM`` :322-347, ``VSSLayer`` :359-410, ``VSSM``
+:423-473, ``PatchEmbed2D`` :54-76, ``PatchMerging2D`` :79-119), so reference checkpoints load with
+``load_state_dict`` and consumers that walk the module tree (``test.py:101``) keep working.
+Parameter initialisation draws from the RNG in the same order as the reference, so
+``torch.manual_seed(s); VSSM(...)`` yields the same random-init weights (checked in
+tests/test_model_cpu.py against the unmodified reference).
+
+What differs is what runs between ``in_proj`` and ``out_proj`` and after the concat: on CUDA the
+hand-written sm_100a kernels behind the C ABI (``medmamba_b200.ops``).  The ``in_proj`` /
+``x_proj`` / ``out_proj`` linears and the CNN branch stay ordinary torch ops (cuBLAS / cuDNN).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.utils.checkpoint as checkpoint
+
+from . import ops
+from .layers import DropPath, trunc_normal_
+from .selective_scan_interface import selective_scan_fn
+
+
+class PatchEmbed2D(nn.Module):
+    """patch_size x patch_size strided conv, NCHW -> NHWC, optional norm (MedMamba.py:54-76)."""
+
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None, **kwargs):
+        super().__init__()
+        ps = (patch_size, patch_size) if isinstance(patch_size, int) else tuple(patch_size)
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=ps, stride=ps)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        x = self.proj(x).permute(0, 2, 3, 1)
+        return x if self.norm is None else self.norm(x)
+
+
+class PatchMerging2D(nn.Module):
+    """2x2 neighbourhood -> channels, LayerNorm(4c), Linear(4c -> 2c) (MedMamba.py:79-119).
+    Odd H / W are truncated like the reference does (MedMamba.py:96-111)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward(self, x):
+        B, H, W, C = x.shape
+        h2, w2 = H // 2, W // 2
+        quads = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
+        x = torch.cat(quads, dim=-1).view(B, h2, w2, 4 * C)
+        return self.reduction(self.norm(x))
+
+
+class SS2D(nn.Module):
+    """2-D selective-scan block (MedMamba.py:123-305).
+
+    ``fused=True`` (default) runs the B200 path: dwconv3x3+SiLU kernel (channels-last) -> one
+    x_proj matmul on un-permuted tokens -> ``ss2d_core`` kernel (4-direction scan with dt_proj,
+    softplus and the cross-merge folded in) -> out_norm * SiLU(z) kernel.  ``fused=False`` follows
+    the reference's op sequence with ``selective_scan_fn`` at the same boundary
+    (``forward_corev0``, the attribute the reference rebinds at MedMamba.py:187).
+    """
+
+    def __init__(self, d_model, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
+                 dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True, bias=False,
+                 device=None, dtype=None, **kwargs):
+        fk = {"device": device, "dtype": dtype}
+        super().__init__()
+        self.d_model = d_model
+        self.d_state = d_state
+        self.d_conv = d_conv
+        self.expand = expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        K, D, N, R = 4, self.d_inner, d_state, self.dt_rank
+
+        self.in_proj = nn.Linear(d_model, 2 * D, bias=bias, **fk)
+        self.conv2d = nn.Conv2d(D, D, kernel_size=d_conv, padding=(d_conv - 1) // 2, groups=D, bias=conv_bias, **fk)
+        self.act = nn.SiLU()
+
+        # K independent x_proj / dt_proj linears, stored stacked (MedMamba.py:164-181)
+        xw = [nn.Linear(D, R + 2 * N, bias=False, **fk).weight for _ in range(K)]
+        self.x_proj_weight = nn.Parameter(torch.stack(xw, dim=0))                      # (K, R+2N, D)
+        dts = [self.dt_init(R, D, dt_scale, dt_init, dt_min, dt_max, dt_init_floor, **fk) for _ in range(K)]
+        self.dt_projs_weight = nn.Parameter(torch.stack([t.weight for t in dts], dim=0))   # (K, D, R)
+        self.dt_projs_bias = nn.Parameter(torch.stack([t.bias for t in dts], dim=0))       # (K, D)
+        self.A_logs = self.A_log_init(N, D, copies=K, merge=True)                      # (K*D, N)
+        self.Ds = self.D_init(D, copies=K, merge=True)                                 # (K*D,)
+
+        self.forward_core = self.forward_corev0
+        self.fused = True
+
+        self.out_norm = nn.LayerNorm(D)
+        self.out_proj = nn.Linear(D, d_model, bias=bias, **fk)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None
+
+    # -- parameter initialisers (MedMamba.py:193-247) ---------------------------------------------
+    @staticmethod
+    def dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4,
+                **factory_kwargs):
+        proj = nn.Linear(dt_rank, d_inner, bias=True, **factory_kwargs)
+        std = dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(proj.weight, -std, std)
+        else:
+            raise NotImplementedError(dt_init)
+        # bias = softplus^-1(dt), dt log-uniform in [dt_min, dt_max]
+        span = math.log(dt_max) - math.log(dt_min)
+        dt = torch.exp(torch.rand(d_inner, **factory_kwargs) * span + math.log(dt_min)).clamp(min=dt_init_floor)
+        with torch.no_grad():
+            proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+        proj.bias._no_reinit = True
+        return proj
+
+    @staticmethod
+    def A_log_init(d_state, d_inner, copies=1, device=None, merge=True):
+        A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32, device=device)).repeat(d_inner, 1)
+        if copies > 1:
+            A_log = A_log.unsqueeze(0).repeat(copies, 1, 1)
+            if merge:
+                A_log = A_log.flatten(0, 1)
+        A_log = nn.Parameter(A_log.contiguous())
+        A_log._no_weight_decay = True
+        return A_log
+
+    @staticmethod
+    def D_init(d_inner, copies=1, device=None, merge=True):
+        D = torch.ones(d_inner, device=device)
+        if copies > 1:
+            D = D.unsqueeze(0).repeat(copies, 1)
+            if merge:
+                D = D.flatten(0, 1)
+        D = nn.Parameter(D.contiguous())
+        D._no_weight_decay = True
+        return D
+
+    # -- reference-order path: materialised cross-scan + selective_scan_fn (MedMamba.py:249-286) --
+    def forward_corev0(self, x: torch.Tensor):
+        self.selective_scan = selective_scan_fn
+        B, C, H, W = x.shape
+        L, K = H * W, 4
+        R, N = self.dt_rank, self.d_state
+        xs = ops.cross_scan(x)                                                        # (B, 4, C, L)
+        x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, self.x_proj_weight)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = torch.einsum("bkrl,kdr->bkdl", dts, self.dt_projs_weight)
+        out_y = self.selective_scan(
+            xs.float().view(B, -1, L), dts.contiguous().float().view(B, -1, L),
+            -torch.exp(self.A_logs.float()).view(-1, N), Bs.float(), Cs.float(), self.Ds.float().view(-1),
+            z=None, delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True,
+            return_last_state=False).view(B, K, -1, L)
+        assert out_y.dtype == torch.float
+        return ops.cross_merge(out_y, H, W)
+
+    def _forward_reference_order(self, x: torch.Tensor):
+        B, H, W, _ = x.shape
+        xz = self.in_proj(x)
+        x, z = xz.chunk(2, dim=-1)
+        x = self.act(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))
+        y1, y2, y3, y4 = self.forward_core(x)
+        assert y1.dtype == torch.float32
+        y = (y1 + y2 + y3 + y4).transpose(1, 2).contiguous().view(B, H, W, -1)
+        y = self.out_norm(y) * F.silu(z)
+        return self.out_proj(y)
+
+    # -- fused B200 path -----------------------------------------------------------------------------
+    def _forward_fused(self, x: torch.Tensor):
+        xz = self.in_proj(x)                                                          # (B, H, W, 2D)
+        y = ops.ss2d_inner(xz, self.conv2d.weight, self.conv2d.bias, self.x_proj_weight, self.dt_projs_weight,
+                           self.dt_projs_bias, self.A_logs, self.Ds, self.out_norm.weight, self.out_norm.bias,
+                           self.out_norm.eps, self.d_state, self.dt_rank)
+        return self.out_proj(y.to(xz.dtype) if y.dtype != xz.dtype else y)
+
+    def forward(self, x: torch.Tensor, **kwargs):
+        use_fused = self.fused and x.is_cuda and self.d_conv == 3 and ops.fused_available()
+        out = self._forward_fused(x) if use_fused else self._forward_reference_order(x)
+        return out if self.dropout is None else self.dropout(out)
+
+
+def channel_shuffle(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """(B, H, W, C): out[..., j*groups + g] = x[..., g*(C/groups) + j] (MedMamba.py:308-320)."""
+    B, H, W, C = x.shape
+    return x.view(B, H, W, groups, C // groups).transpose(3, 4).reshape(B, H, W, C)
+
+
+class SS_Conv_SSM(nn.Module):
+    """Half the channels through LN -> SS2D, half through a small CNN, interleaved back together
+    with a residual (MedMamba.py:322-357)."""
+
+    def __init__(self, hidden_dim: int = 0, drop_path: float = 0,
+                 norm_layer: Callable[..., nn.Module] = None, attn_drop_rate: float = 0, d_state: int = 16,
+                 **kwargs):
+        super().__init__()
+        if norm_layer is None:
+            norm_layer = lambda c: nn.LayerNorm(c, eps=1e-6)
+        c = hidden_dim // 2
+        self.ln_1 = norm_layer(c)
+        self.self_attention = SS2D(d_model=c, dropout=attn_drop_rate, d_state=d_state, **kwargs)
+        self.drop_path = DropPath(drop_path)
+        self.conv33conv33conv11 = nn.Sequential(
+            nn.BatchNorm2d(c),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=1, stride=1),
+            nn.ReLU(),
+        )
+
+    def forward(self, input: torch.Tensor):
+        left, right = input.chunk(2, dim=-1)
+        ssm = self.drop_path(self.self_attention(self.ln_1(right)))
+        # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
+        left = self.conv33conv33conv11(left.permute(0, 3, 1, 2))
+        left = left.permute(0, 2, 3, 1)
+        if input.is_cuda and ops.fused_available():
+            return ops.shuffle_cat_residual(left, ssm, input)
+        return channel_shuffle(torch.cat((left, ssm), dim=-1), groups=2) + input
+
+
+class VSSLayer(nn.Module):
+    """One stage: ``depth`` blocks and an optional downsample (MedMamba.py:359-422)."""
+
+    def __init__(self, dim, depth, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None,
+                 use_checkpoint=False, d_state=16, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SS_Conv_SSM(hidden_dim=dim, drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                        norm_layer=norm_layer, attn_drop_rate=attn_drop, d_state=d_state)
+            for i in range(depth)])
+        # The reference re-initialises a *clone* of every out_proj.weight here (MedMamba.py:398-404):
+        # no parameter changes, but the RNG advances.  Reproduced so seeds give identical weights.
+        for blk in self.blocks:
+            nn.init.kaiming_uniform_(blk.self_attention.out_proj.weight.detach().clone(), a=math.sqrt(5))
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = checkpoint.checkpoint(blk, x) if self.use_checkpoint else blk(x)
+        return x if self.downsample is None else self.downsample(x)
+
+
+class VSSM(nn.Module):
+    """MedMamba backbone + classifier head (MedMamba.py:423-515).  MedMamba-T is
+    ``VSSM(depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], num_classes=...)`` (train.py:179)."""
+
+    def __init__(self, patch_size=4, in_chans=3, num_classes=1000, depths=[2, 2, 4, 2],
+                 dims=[96, 192, 384, 768], d_state=16, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1,
+                 norm_layer=nn.LayerNorm, patch_norm=True, use_checkpoint=False, **kwargs):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_layers = len(depths)
+        if isinstance(dims, int):
+            dims = [int(dims * 2 ** i) for i in range(self.num_layers)]
+        self.embed_dim = dims[0]
+        self.num_features = dims[-1]
+        self.dims = dims
+
+        self.patch_embed = PatchEmbed2D(patch_size=patch_size, in_chans=in_chans, embed_dim=self.embed_dim,
+                                        norm_layer=norm_layer if patch_norm else None)
+        self.ape = False
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            lo, hi = sum(depths[:i]), sum(depths[:i + 1])
+            self.layers.append(VSSLayer(
+                dim=dims[i], depth=depths[i], d_state=math.ceil(dims[0] / 6) if d_state is None else d_state,
+                drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[lo:hi], norm_layer=norm_layer,
+                downsample=PatchMerging2D if i < self.num_layers - 1 else None, use_checkpoint=use_checkpoint))
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+
+        self.apply(self._init_weights)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def _init_weights(self, m: nn.Module):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"absolute_pos_embed"}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {"relative_position_bias_table"}
+
+    def forward_backbone(self, x):
+        x = self.pos_drop(self.patch_embed(x))
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def forward(self, x):
+        x = self.forward_backbone(x)                       # (B, H, W, C)
+        x = self.avgpool(x.permute(0, 3, 1, 2))
+        return self.head(torch.flatten(x, start_dim=1))
+
+
+def medmamba_t(num_classes=6, **kw):
+    return VSSM(depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], num_classes=num_classes, **kw)
+
+
+def medmamba_s(num_classes=6, **kw):
+    return VSSM(depths=[2, 2, 8, 2], dims=[96, 192, 384, 768], num_classes=num_classes, **kw)
+
+
+def medmamba_b(num_classes=6, **kw):
+    return VSSM(depths=[2, 2, 12, 2], dims=[128, 256, 512, 1024], num_classes=num_classes, **kw)

@@ -1,0 +1,162 @@
+"""Python face of the fused SS2D kernels (thin ctypes calls into libmedmamba_b200.so).
+
+Everything here is channels-last and indexed by token position; see include/medmamba_b200.h for
+the contract of each entry point and DESIGN.md for the data layout.  CUDA only -- no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from ._lib import check, dtype_code, i64, lib, ptr, require_cuda, stream_ptr
+
+_c_int = ctypes.c_int
+
+
+def fused_available() -> bool:
+    """True when the CUDA library is loadable (it is built on demand; failure raises)."""
+    lib()
+    return True
+
+
+# ------------------------------------------------------------------------ reference-order helpers
+def cross_scan(x: torch.Tensor) -> torch.Tensor:
+    """(B, D, H, W) -> (B, 4, D, L): row-major, column-major and both reversed (MedMamba.py:256-257)."""
+    B, D, H, W = x.shape
+    hw = x.flatten(2)
+    wh = x.transpose(2, 3).flatten(2)
+    fwd = torch.stack((hw, wh), dim=1)
+    return torch.cat((fwd, fwd.flip(-1)), dim=1)
+
+
+def cross_merge(out_y: torch.Tensor, H: int, W: int):
+    """(B, 4, D, L) -> the reference's four position-ordered tensors (MedMamba.py:282-286)."""
+    B, K, D, L = out_y.shape
+    back = out_y[:, 2:4].flip(-1)
+    y_wh = out_y[:, 1].view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+    y_invwh = back[:, 1].view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+    return out_y[:, 0], back[:, 0], y_wh, y_invwh
+
+
+# ------------------------------------------------------------------------ raw kernel launchers
+def dt_pad(dt_rank: int) -> int:
+    rp = lib().mmb_ss2d_core_dt_pad(_c_int(dt_rank))
+    if rp < 0:
+        raise ValueError(f"dt_rank {dt_rank} is not supported by the fused SS2D kernel (max 32)")
+    return rp
+
+
+def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    """x: (B, H, W, D) channels-last view (channel stride 1, uniform pixel pitch) -> dense fp32."""
+    dev = require_cuda(x, weight, bias)
+    B, H, W, D = x.shape
+    if x.stride(3) != 1 or x.stride(1) != W * x.stride(2):
+        x = x.contiguous()
+    out = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+    w = weight.detach().float().contiguous()
+    bs = bias.detach().float().contiguous() if bias is not None else None
+    with torch.cuda.device(dev):
+        st = lib().mmb_dwconv3x3_silu_fwd(ptr(x), ptr(w), ptr(bs), ptr(out), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
+                                          i64(x.stride(2)), i64(x.stride(0)), _c_int(dtype_code(x)),
+                                          _c_int(dtype_code(out)), stream_ptr(dev))
+    check(st, "mmb_dwconv3x3_silu_fwd")
+    return out
+
+
+def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int) -> torch.Tensor:
+    """xc (B, H, W, D) fp32, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) fp32."""
+    dev = require_cuda(xc, proj, Wdt, dt_bias, A, Ds)
+    B, H, W, D = xc.shape
+    rp = dt_pad(dt_rank)
+    assert proj.shape == (B, H, W, 4, 32 + rp) and proj.is_contiguous() and xc.is_contiguous()
+    ydir = torch.empty((B, H, W, 4, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir),
+                                     _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
+                                     _c_int(rp), stream_ptr(dev))
+    check(st, "mmb_ss2d_core_fwd")
+    return ydir
+
+
+def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
+    """ydir (B, H, W, 4, D) fp32, z (B, H, W, D) view -> LayerNorm(sum of directions) * SiLU(z)."""
+    dev = require_cuda(ydir, z, gamma, beta)
+    B, H, W, K, D = ydir.shape
+    if z.stride(3) != 1 or z.stride(1) != W * z.stride(2) or z.stride(0) != H * W * z.stride(2):
+        z = z.contiguous()
+    out = torch.empty((B, H, W, D), dtype=z.dtype, device=dev)
+    merged = torch.empty((B, H, W, D), dtype=torch.float32, device=dev) if want_merged else None
+    g = gamma.detach().float().contiguous()
+    bt = beta.detach().float().contiguous()
+    with torch.cuda.device(dev):
+        st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged), i64(B * H * W),
+                                        _c_int(D), i64(z.stride(2)), ctypes.c_float(eps), _c_int(dtype_code(z)),
+                                        _c_int(dtype_code(out)), stream_ptr(dev))
+    check(st, "mmb_outnorm_gate_fwd")
+    return (out, merged) if want_merged else out
+
+
+def _token_view(t: torch.Tensor):
+    """(B, H, W, C) with channel stride 1 and a uniform pixel pitch, else a dense copy."""
+    B, H, W, C = t.shape
+    px = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != W * px or t.stride(0) != H * W * px:
+        t = t.contiguous()
+    return t, t.stride(2)
+
+
+def shuffle_cat_residual_raw(left, ssm, inp) -> torch.Tensor:
+    dev = require_cuda(left, ssm, inp)
+    B, H, W, c = ssm.shape
+    dt = inp.dtype
+    left, lp = _token_view(left.to(dt))
+    ssm, sp = _token_view(ssm.to(dt))
+    inp, ip = _token_view(inp)
+    out = torch.empty((B, H, W, 2 * c), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().mmb_shuffle_cat_residual_fwd(ptr(left), ptr(ssm), ptr(inp), ptr(out), i64(B * H * W), _c_int(c),
+                                                i64(lp), i64(sp), i64(ip), _c_int(dtype_code(inp)), stream_ptr(dev))
+    check(st, "mmb_shuffle_cat_residual_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------ weight packing
+def pack_x_proj(x_proj_weight: torch.Tensor, d_state: int, dt_rank: int) -> torch.Tensor:
+    """(4, R+2N, D) -> (4*(32+RP), D): per direction rows [B_n (16) | C_n (16) | dt_r (RP)], zero padded.
+    Built with differentiable torch ops, so autograd carries the gradient back to x_proj_weight."""
+    K, _, D = x_proj_weight.shape
+    R, N, rp = dt_rank, d_state, dt_pad(dt_rank)
+    w_dt, w_B, w_C = torch.split(x_proj_weight, [R, N, N], dim=1)
+    pad = lambda t, n: F.pad(t, (0, 0, 0, n - t.shape[1]))
+    return torch.cat((pad(w_B, 16), pad(w_C, 16), pad(w_dt, rp)), dim=1).reshape(K * (32 + rp), D)
+
+
+# ------------------------------------------------------------------------ composed forward (no autograd yet)
+def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
+               eps, d_state, dt_rank):
+    """Everything between in_proj and out_proj of SS2D.forward (MedMamba.py:292-301).
+    xz: (B, H, W, 2D) -> gated, normalised y (B, H, W, D) in xz.dtype."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (xz, conv_w, x_proj_weight, dt_projs_weight,
+                                                                  dt_projs_bias, A_logs, Ds, norm_w, norm_b)):
+        from .fused_autograd import ss2d_inner_autograd
+        return ss2d_inner_autograd(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds,
+                                   norm_w, norm_b, eps, d_state, dt_rank)
+    B, H, W, D2 = xz.shape
+    D = D2 // 2
+    x, z = xz[..., :D], xz[..., D:]
+    xc = dwconv3x3_silu(x, conv_w, conv_b)
+    w_packed = pack_x_proj(x_proj_weight.float(), d_state, dt_rank)
+    proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+    A = -torch.exp(A_logs.float())
+    ydir = ss2d_core(xc, proj, dt_projs_weight.float().contiguous(), dt_projs_bias.float().contiguous(),
+                     A.contiguous(), Ds.float().contiguous(), d_state, dt_rank)
+    return outnorm_gate(ydir, z, norm_w, norm_b, eps)
+
+
+def shuffle_cat_residual(left, ssm, inp):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (left, ssm, inp)):
+        from .fused_autograd import shuffle_cat_residual_autograd
+        return shuffle_cat_residual_autograd(left, ssm, inp)
+    return shuffle_cat_residual_raw(left, ssm, inp)

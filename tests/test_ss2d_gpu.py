@@ -1,0 +1,156 @@
+"""Parity of the fused SS2D path (CUDA, through the C ABI) with the oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cscan, medmamba_ref
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _cases(d):
+    names = sorted({k.split(".")[0] for k in d})
+    return {n: {k[len(n) + 1:]: v for k, v in d.items() if k.startswith(n + ".")} for n in names}
+
+
+def cscan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    out, last = cscan.scan_fwd(u, delta, A, B.contiguous(), C.contiguous(), D, z, delta_bias, delta_softplus,
+                               precision="f64")
+    return (out.float(), last) if return_last_state else out.float()
+
+
+@pytest.mark.parametrize("B,H,W,D", [(1, 1, 1, 4), (2, 5, 7, 16), (3, 8, 8, 96), (2, 14, 14, 384), (1, 7, 3, 40),
+                                      (2, 56, 56, 96)])
+def test_dwconv_silu(B, H, W, D):
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(D + H)
+    xz = torch.randn(B, H, W, 2 * D, generator=g)
+    w = torch.randn(D, 1, 3, 3, generator=g) * 0.5
+    bias = torch.randn(D, generator=g)
+    want = F.silu(F.conv2d(xz[..., :D].permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1, groups=D))
+    got = ops.dwconv3x3_silu(xz.cuda()[..., :D], w.cuda(), bias.cuda())
+    assert got.shape == (B, H, W, D)
+    assert_close(got.permute(0, 3, 1, 2), want, 1e-5, 1e-6, "dwconv+silu")
+    got = ops.dwconv3x3_silu(xz.cuda()[..., :D], w.cuda(), None)
+    want = F.silu(F.conv2d(xz[..., :D].permute(0, 3, 1, 2).double(), w.double(), None, padding=1, groups=D))
+    assert_close(got.permute(0, 3, 1, 2), want, 1e-5, 1e-6, "dwconv+silu no bias")
+
+
+@pytest.mark.parametrize("B,H,W,c", [(1, 1, 1, 4), (2, 5, 7, 8), (2, 14, 14, 192), (3, 9, 4, 20)])
+def test_shuffle_cat_residual_bit_exact(B, H, W, c):
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(c)
+    left, ssm, inp = torch.randn(B, H, W, c, generator=g), torch.randn(B, H, W, c, generator=g), torch.randn(B, H, W, 2 * c, generator=g)
+    want = medmamba_ref.channel_shuffle(torch.cat((left, ssm), -1), 2) + inp
+    got = ops.shuffle_cat_residual(left.cuda(), ssm.cuda(), inp.cuda())
+    assert torch.equal(got.cpu(), want)
+    # left arriving as the permuted view of an NCHW tensor (what the CNN branch returns)
+    got = ops.shuffle_cat_residual(left.permute(0, 3, 1, 2).contiguous().cuda().permute(0, 2, 3, 1), ssm.cuda(), inp.cuda())
+    assert torch.equal(got.cpu(), want)
+
+
+def _random_ss2d_params(D, R, N, seed, stress):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    sc = 1.0 if stress else 0.3
+    return dict(
+        x_proj_weight=rn(4, R + 2 * N, D) * sc / D ** 0.5,
+        dt_projs_weight=rn(4, D, R) * R ** -0.5,
+        dt_projs_bias=rn(4, D) - 3.0,
+        A_logs=torch.log(torch.arange(1, N + 1).float()).repeat(4 * D, 1) + (0.3 * rn(4 * D, N) if stress else 0),
+        Ds=1.0 + (rn(4 * D) if stress else 0),
+    )
+
+
+@pytest.mark.parametrize("B,H,W,D,R,N,stress", [
+    (2, 1, 1, 8, 1, 16, True), (2, 5, 7, 16, 1, 16, True), (1, 3, 9, 40, 3, 16, True), (2, 7, 7, 768, 24, 16, True),
+    (2, 14, 14, 384, 12, 16, True), (3, 28, 28, 192, 6, 16, True), (2, 56, 56, 96, 3, 16, True),
+    (8, 56, 56, 96, 3, 16, False), (64, 7, 7, 768, 24, 16, False), (2, 33, 5, 24, 2, 8, True), (1, 40, 70, 8, 1, 16, True),
+])
+def test_core_directions_vs_oracle(B, H, W, D, R, N, stress):
+    """ydir[..., k, :] equals the reference's y1..y4 (MedMamba.py:286) in the order (y1, y3, y2, y4)."""
+    from medmamba_b200 import ops
+    prm = _random_ss2d_params(D, R, N, seed=H * W + D, stress=stress)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, D, H, W, generator=g) * (1.0 if stress else 0.1)     # conv output, NCHW like the reference
+    ys = medmamba_ref.ss2d_core(x, prm["x_proj_weight"], prm["dt_projs_weight"], prm["dt_projs_bias"],
+                                prm["A_logs"], prm["Ds"], scan_fn=cscan_fn)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.pack_x_proj(prm["x_proj_weight"].cuda(), N, R)
+    proj = (xc.view(-1, D) @ wp.t()).view(B, H, W, 4, -1)
+    ydir = ops.ss2d_core(xc, proj, prm["dt_projs_weight"].cuda().contiguous(), prm["dt_projs_bias"].cuda().contiguous(),
+                         (-torch.exp(prm["A_logs"])).cuda().contiguous(), prm["Ds"].cuda().contiguous(), N, R)
+    torch.cuda.synchronize()
+    assert ydir.shape == (B, H, W, 4, D)
+    for k, ref_i in enumerate([0, 2, 1, 3]):
+        want = ys[ref_i].reshape(B, D, H, W).permute(0, 2, 3, 1)
+        scale = max(1.0, want.abs().max().item())
+        assert_close(ydir[..., k, :].cpu() / scale, want / scale, 1e-4, 1e-5, f"direction {k}")
+        uD = (x * prm["Ds"].view(4, D)[k].view(1, D, 1, 1)).permute(0, 2, 3, 1)
+        assert_close((ydir[..., k, :].cpu() - uD) / scale, (want - uD) / scale, 1e-4, 1e-5, f"direction {k} minus u*D")
+
+
+def test_outnorm_gate():
+    from medmamba_b200 import ops
+    for (B, H, W, D) in [(2, 3, 5, 8), (2, 14, 14, 384), (1, 7, 7, 768), (2, 9, 9, 96), (1, 2, 2, 1024)]:
+        g = torch.Generator().manual_seed(D)
+        ydir = torch.randn(B, H, W, 4, D, generator=g)
+        xz = torch.randn(B, H, W, 2 * D, generator=g)
+        gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+        y = ((ydir[..., 0, :] + ydir[..., 2, :]) + ydir[..., 1, :]) + ydir[..., 3, :]
+        want = F.layer_norm(y.double(), (D,), gamma.double(), beta.double(), 1e-5) * F.silu(xz[..., D:].double())
+        got, merged = ops.outnorm_gate(ydir.cuda(), xz.cuda()[..., D:], gamma.cuda(), beta.cuda(), 1e-5, want_merged=True)
+        assert torch.equal(merged.cpu(), y)         # the merge order is the reference's, bit for bit
+        assert_close(got, want, 1e-5, 1e-5, "out_norm * silu(z)")
+
+
+def test_ss2d_module_vs_golden():
+    import medmamba_b200 as mm
+    for name, c in _cases(_load("ss2d_small.npz")).items():
+        sd = {k[3:]: v for k, v in c.items() if k.startswith("sd.")}
+        d_model = c["x"].shape[-1]
+        m = mm.SS2D(d_model=d_model).cuda().eval()
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            y_fused = m(c["x"].cuda())
+            m.fused = False
+            y_unfused = m(c["x"].cuda())
+        assert_close(y_fused, c["y"], 1e-4, 1e-5, f"fused SS2D {name}")
+        assert_close(y_unfused, c["y"], 1e-4, 1e-5, f"reference-order SS2D {name}")
+
+
+def test_vssm_tiny_vs_golden():
+    import medmamba_b200 as mm
+    c = _load("vssm_tiny.npz")
+    sd = {k[3:]: v for k, v in c.items() if k.startswith("sd.")}
+    net = mm.VSSM(depths=[int(v) for v in c["depths"]], dims=[int(v) for v in c["dims"]], num_classes=5)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        logits = net(c["x"].cuda())
+    assert_close(logits, c["logits"], 1e-4, 1e-4, "tiny VSSM logits")
+    assert torch.equal(logits.argmax(1).cpu(), c["logits"].argmax(1))
+
+
+def test_vssm_t_config1_logits_and_top1():
+    """BASELINE config 1: MedMamba-T fp32 forward, batch 8, 224x224, against the reference's logits."""
+    import medmamba_b200 as mm
+    g = _load("vssm_t_config1.npz")
+    torch.manual_seed(int(g["weight_seed"]))
+    net = mm.medmamba_t(num_classes=6).cuda().eval()
+    torch.manual_seed(int(g["input_seed"]))
+    x = torch.randn(8, 3, 224, 224)
+    with torch.no_grad():
+        logits = net(x.cuda())
+    assert_close(logits, g["logits"], 1e-3, 1e-4, "config-1 logits")
+    assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
