@@ -12,19 +12,23 @@
 // Direction k walks the positions in the order of SURVEY.md Appendix A (row-major, column-major
 // and their reverses), so no flipped or transposed copy of anything is ever materialised.
 //
-// One CTA owns (batch b, direction k, CT channels) for the whole sequence: a producer warp streams
-// blocks of consecutive steps of xc and proj into a shared-memory ring with TMA tensor copies
-// (a row block for k = 0, 2; a column block for k = 1, 3) signalled through mbarriers; the
-// consumer warps hold one channel per S lanes with the 16/S states of the lane in registers.
+// One CTA owns (batch b, direction k, CT channels) for the whole sequence.  Blocks of <= 32
+// consecutive steps of xc and proj are streamed into a shared-memory ring with TMA tensor copies
+// (a row block for k = 0, 2; a column block for k = 1, 3) signalled through mbarriers; thread 0
+// re-arms a stage as soon as every warp has released it (no dedicated producer warp: its
+// registers would be a quarter of the register file at 3 warps per CTA).  Every warp holds one
+// channel per S lanes with the 16/S states of the lane in registers.
 // Per step and state: one MUFU.EX2 and four FMA-pipe operations; the kernel is bound by the
 // 16 exp/clk/SM MUFU rate, not by HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 
 namespace mmb {
 
 constexpr int kCoreStages = 4;
-constexpr int kCoreStageBytes = 24 * 1024;
+constexpr int kCoreStageBytes = 16 * 1024;
 
 struct CoreFwdParams {
     float* ydir;
@@ -36,10 +40,12 @@ struct CoreFwdParams {
     int T_row, NB_row;                 // row view: NB_row blocks of T_row consecutive positions
     int nw, T_col, NI_col, NO_col;     // column view: NO_col column groups x NI_col row blocks
     int cap;                           // steps a stage can hold
+    int kmask;                         // debug: directions to run (bit k); 15 in production
+    int dbg;                           // debug flags: 1 = try_wait instead of polling, 2 = skip stores, 4 = skip compute
 };
 
 template <int S, int RP>
-__global__ void __launch_bounds__(416)
+__global__ void __launch_bounds__(384)
 ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
                      const CoreFwdParams p) {
@@ -54,44 +60,39 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     uint64_t* empty = full + kCoreStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ncons = (blockDim.x >> 5) - 1;
+    const int nwarps = blockDim.x >> 5;
     const int k = blockIdx.y, b = blockIdx.z, c0 = blockIdx.x * p.CT;
     const bool colview = (k & 1) != 0, rev = k >= 2;
     const int NB = colview ? p.NO_col * p.NI_col : p.NB_row;
+    if (!((p.kmask >> k) & 1)) return;
+
+    // Block jb (time order) -> TMA loads into stage jb % kCoreStages; issued by thread 0 only.
+    auto issue = [&](int jb) {
+        const int s = jb % kCoreStages;
+        const int blk = rev ? NB - 1 - jb : jb;
+        uint8_t* xs = smem_raw + s * (xpad + ppad);
+        uint8_t* ps = xs + xpad;
+        if (!colview) {
+            mbar_expect_tx(&full[s], p.T_row * (p.CT + CP) * 4);
+            tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
+            tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
+        } else {
+            const int o = blk / p.NI_col, i = blk % p.NI_col;
+            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT + CP) * 4);
+            tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
+            tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
+        }
+    };
 
     if (tid == 0) {
-        for (int s = 0; s < kCoreStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncons); }
+        prefetch_tmap(colview ? &tmx_col : &tmx_row);
+        prefetch_tmap(colview ? &tmp_col : &tmp_row);
+        for (int s = 0; s < kCoreStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
         mbar_fence_init();
+        for (int jb = 0; jb < kCoreStages - 1 && jb < NB; ++jb) issue(jb);
     }
     __syncthreads();
 
-    if (warp == ncons) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            prefetch_tmap(colview ? &tmx_col : &tmx_row);
-            prefetch_tmap(colview ? &tmp_col : &tmp_row);
-            for (int j = 0; j < NB; ++j) {
-                const int s = j % kCoreStages, ph = (j / kCoreStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int blk = rev ? NB - 1 - j : j;
-                uint8_t* xs = smem_raw + s * (xpad + ppad);
-                uint8_t* ps = xs + xpad;
-                if (!colview) {
-                    mbar_expect_tx(&full[s], p.T_row * (p.CT + CP) * 4);
-                    tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
-                    tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
-                } else {
-                    const int o = blk / p.NI_col, i = blk % p.NI_col;
-                    mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT + CP) * 4);
-                    tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
-                    tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- consumers
     const int t = warp * 32 + lane;
     const int cl = t / S, q = t % S;            // channel inside the tile, state split index
     const int c = c0 + cl;
@@ -111,11 +112,20 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     const float bias = cvalid ? p.bias[row] : 0.f;
     const float Dd = cvalid ? p.Ds[row] : 0.f;
     float* yb = p.ydir + ((int64_t)b * p.L * 4 + k) * p.D + c;   // + pos * 4 * D
+    const int64_t ystride = 4 * (int64_t)p.D;
 
     for (int jb = 0; jb < NB; ++jb) {
         const int s = jb % kCoreStages, ph = (jb / kCoreStages) & 1;
+        // refill the stage block jb-1 has just left (inline producer: one thread)
+        if (tid == 0 && jb + kCoreStages - 1 < NB) {
+            const int jn = jb + kCoreStages - 1;
+            if (jb > 0) mbar_wait(&empty[jn % kCoreStages], ((jb - 1) / kCoreStages) & 1);
+            issue(jn);
+        }
+        __syncwarp();
         const int blk = rev ? NB - 1 - jb : jb;
-        // geometry of the block: nrows x ncols positions, slot = hh*nwbox + ww, pos = pbase + hh*psh + ww
+        // geometry: nrows x ncols positions, column-major in time; lane ti owns the slot / position
+        // of the block's ti-th step in forward order (a block never has more than 32 steps)
         int nrows, ncols, nwbox, psh, pbase;
         if (!colview) {
             pbase = blk * p.T_row; nrows = min(p.T_row, p.L - pbase); ncols = 1; nwbox = 1; psh = 1;
@@ -126,35 +136,41 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             pbase = h0 * p.W + w0;
         }
         const int nsteps = nrows * ncols;
-        const float* xs = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad));
+        int slot_l = 0, pos_l = 0;
+        if (lane < nsteps) {
+            const int ww = lane / nrows, hh = lane - ww * nrows;
+            slot_l = hh * nwbox + ww;
+            pos_l = pbase + hh * psh + ww;
+        }
+        const float* xs = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad)) + cl;
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
-        mbar_wait(&full[s], ph);
+        if (p.dbg & 1) { while (!mbar_try_wait(&full[s], ph)) {} } else mbar_wait(&full[s], ph);
 
-        int ww = rev ? ncols - 1 : 0, hh = rev ? nrows - 1 : 0;   // position of the next step in time order
-        for (int g0 = 0; g0 < nsteps; g0 += 4) {
+        for (int g0 = 0; g0 < ((p.dbg & 4) ? 0 : nsteps); g0 += 4) {
             int slot[4], pos[4];
             bool ok[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ok[i] = g0 + i < nsteps;
-                slot[i] = ok[i] ? hh * nwbox + ww : 0;
-                pos[i] = pbase + hh * psh + ww;
-                if (!rev) { if (++hh == nrows) { hh = 0; ++ww; } }
-                else      { if (--hh < 0) { hh = nrows - 1; --ww; } }
+                const int tl = g0 + i;
+                ok[i] = tl < nsteps;
+                const int ti = ok[i] ? (rev ? nsteps - 1 - tl : tl) : 0;
+                slot[i] = __shfl_sync(0xffffffffu, slot_l, ti);
+                pos[i] = __shfl_sync(0xffffffffu, pos_l, ti);
             }
-            // u of the four steps (all S lanes of a channel read the same word)
             float uu[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? xs[slot[i] * p.CT + cl] : 0.f;
+            for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? xs[slot[i] * p.CT] : 0.f;
             // delta = softplus(Wdt . dt_r + bias): each lane evaluates OWN of the four steps
             float down[OWN];
 #pragma unroll
             for (int m = 0; m < OWN; ++m) {
-                const int i = q + S * m;            // step handled by this lane
-                // slot[i] with a lane-dependent i: select without dynamic register indexing
-                int sl = slot[0]; bool okk = ok[0];
-#pragma unroll
-                for (int ii = 1; ii < 4; ++ii) if (ii == i) { sl = slot[ii]; okk = ok[ii]; }
+                int sl; bool okk;
+                if (S == 1) { sl = slot[m]; okk = ok[m]; }
+                else {
+                    const int tl = g0 + q + S * m;
+                    okk = tl < nsteps;
+                    sl = __shfl_sync(0xffffffffu, slot_l, okk ? (rev ? nsteps - 1 - tl : tl) : 0);
+                }
                 const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
                 float acc0 = bias, acc1 = 0.f;
 #pragma unroll
@@ -168,11 +184,10 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             float dl[4], du[4], y[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                dl[i] = S == 1 ? down[i] : __shfl_sync(0xffffffffu, down[i / S], lane_base + (i % S));
+                dl[i] = S == 1 ? down[i / S] : __shfl_sync(0xffffffffu, down[i / S], lane_base + (i % S));
                 du[i] = dl[i] * uu[i];
                 y[i] = 0.f;
             }
-            // recurrence
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4* bp = reinterpret_cast<const float4*>(ps + slot[i] * CP) + q;
@@ -197,7 +212,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (ok[i] && cvalid && q == (i % S)) yb[(int64_t)pos[i] * 4 * p.D] = fmaf(Dd, uu[i], y[i]);
+                if (ok[i] && cvalid && q == (i % S) && !(p.dbg & 2)) yb[pos[i] * ystride] = fmaf(Dd, uu[i], y[i]);
             }
         }
         __syncwarp();
@@ -212,9 +227,10 @@ struct CorePlan {
 
 static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
     const long rows = 4L * B * D;
-    const long want = 32L * 16 * num_sms();
+    const long want = 32L * 12 * num_sms();
     int S = 1;
     while (S < 4 && rows * S < want) S *= 2;
+    if (const char* e = getenv("MMB_CORE_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int gran = 32 / S;                          // channels per warp
     int capc = 256 < 384 / S ? 256 : 384 / S;
     capc -= capc % gran;
@@ -225,6 +241,7 @@ static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
     const int CP = 32 + RP;
     int cap = kCoreStageBytes / ((CT + CP) * 4);
     if (cap > 32) cap = 32;
+    if (const char* e = getenv("MMB_CORE_CAP")) { const int v = atoi(e); if (v >= 4 && v <= 32 && v < cap) cap = v; }
     if (cap < 4) return false;
     const int L = H * W;
     pl.NB_row = (L + cap - 1) / cap;
@@ -242,7 +259,7 @@ static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
     if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256 || CT > 256) return false;
     pl.cap = pl.T_row > pl.nw * pl.T_col ? pl.T_row : pl.nw * pl.T_col;
     pl.S = S; pl.CT = CT; pl.tiles = tiles;
-    pl.threads = (CT * S / 32 + 1) * 32;
+    pl.threads = CT * S;
     const size_t xpad = ((size_t)pl.cap * CT * 4 + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
     pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
     return true;
@@ -315,6 +332,10 @@ extern "C" int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank; p.CT = pl.CT;
     p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
     p.cap = pl.cap;
+    p.kmask = 15;
+    if (const char* e = getenv("MMB_CORE_KMASK")) p.kmask = atoi(e);
+    p.dbg = 0;
+    if (const char* e = getenv("MMB_CORE_DBG")) p.dbg = atoi(e);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (dt_pad) {
         case 4: return dispatch_core_s<4>(pl, p, xc, proj, st);

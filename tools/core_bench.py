@@ -1,0 +1,46 @@
+"""Times the fused SS2D core kernel alone at the MedMamba-T stage shapes (CUDA events, L2 flushed)."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from medmamba_b200 import ops
+
+STAGES = [(56, 56, 96, 3), (28, 28, 192, 6), (14, 14, 384, 12), (7, 7, 768, 24)]
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--stage", type=int, default=-1)
+ap.add_argument("--noflush", action="store_true")
+args = ap.parse_args()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for si, (H, W, D, R) in enumerate(STAGES):
+    if args.stage >= 0 and si != args.stage:
+        continue
+    B, N = args.batch, 16
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xc = 0.1 * torch.randn(B, H, W, D, device="cuda", generator=g)
+    rp = ops.dt_pad(R)
+    proj = 0.05 * torch.randn(B, H, W, 4, 32 + rp, device="cuda", generator=g)
+    Wdt = torch.randn(4, D, R, device="cuda", generator=g) * R ** -0.5
+    bias = torch.full((4, D), -4.6, device="cuda")
+    A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(4 * D, 1).contiguous()
+    Ds = torch.ones(4 * D, device="cuda")
+    run = lambda: ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.iters):
+        if not args.noflush:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    exps = B * 4 * D * H * W * 16
+    fused_bytes = 4 * B * H * W * (2 * D + 4 * (R + 32))
+    iface_bytes = 4 * B * H * W * (3 * 4 * D + 2 * 4 * 16)
+    print(json.dumps(dict(stage=si + 1, batch=B, ms=round(ms, 4), min_ms=round(ts[0], 4),
+                          Gexp_s=round(exps / ms / 1e6, 1), mufu_frac=round(exps / ms / 1e6 / 4653, 3),
+                          fused_GBs=round(fused_bytes / ms / 1e6, 1), iface_GBs=round(iface_bytes / ms / 1e6, 1),
+                          env={k: v for k, v in os.environ.items() if k.startswith("MMB_")})))
