@@ -30,6 +30,24 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// Packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): two FMAs per issue slot.  The scan's inner loop is
+// bound by issue slots and MUFU, not by FMA-pipe lanes, so halving the instruction count of the
+// state update pays directly.  Operands are passed as scalars; ptxas allocates aligned pairs.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // softplus(x) = log1p(exp(x)), identity above 20 (torch F.softplus defaults; temp.py:63-64).
 // v = e^x; below 1/8 the alternating series (rel. error < 1e-7), above it lg2(1+v) whose
 // absolute error (2^-22) is then small against the result.

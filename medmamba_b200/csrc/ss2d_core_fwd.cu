@@ -22,6 +22,8 @@
 // 16 exp/clk/SM MUFU rate, not by HBM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -41,7 +43,7 @@ struct CoreFwdParams {
     int nw, T_col, NI_col, NO_col;     // column view: NO_col column groups x NI_col row blocks
     int cap;                           // steps a stage can hold
     int kmask;                         // debug: directions to run (bit k); 15 in production
-    int dbg;                           // debug flags: 1 = try_wait instead of polling, 2 = skip stores, 4 = skip compute
+    int dbg;                           // debug flags: 1 = try_wait instead of polling
 };
 
 template <int S, int RP>
@@ -146,13 +148,15 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
         if (p.dbg & 1) { while (!mbar_try_wait(&full[s], ph)) {} } else mbar_wait(&full[s], ph);
 
-        for (int g0 = 0; g0 < ((p.dbg & 4) ? 0 : nsteps); g0 += 4) {
+        // One group = four consecutive steps.  FULL groups carry no per-step validity predicates.
+        auto group = [&](auto full_tag, const int g0) {
+            constexpr bool FULL = decltype(full_tag)::value;
             int slot[4], pos[4];
             bool ok[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int tl = g0 + i;
-                ok[i] = tl < nsteps;
+                ok[i] = FULL || tl < nsteps;
                 const int ti = ok[i] ? (rev ? nsteps - 1 - tl : tl) : 0;
                 slot[i] = __shfl_sync(0xffffffffu, slot_l, ti);
                 pos[i] = __shfl_sync(0xffffffffu, pos_l, ti);
@@ -168,7 +172,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 if (S == 1) { sl = slot[m]; okk = ok[m]; }
                 else {
                     const int tl = g0 + q + S * m;
-                    okk = tl < nsteps;
+                    okk = FULL || tl < nsteps;
                     sl = __shfl_sync(0xffffffffu, slot_l, okk ? (rev ? nsteps - 1 - tl : tl) : 0);
                 }
                 const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
@@ -176,34 +180,39 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
 #pragma unroll
                 for (int r4 = 0; r4 < RP / 4; ++r4) {
                     const float4 v = dtp[r4];
-                    acc0 = fmaf(Wd[4 * r4 + 0], v.x, acc0); acc1 = fmaf(Wd[4 * r4 + 1], v.y, acc1);
-                    acc0 = fmaf(Wd[4 * r4 + 2], v.z, acc0); acc1 = fmaf(Wd[4 * r4 + 3], v.w, acc1);
+                    fma2(acc0, acc1, Wd[4 * r4 + 0], Wd[4 * r4 + 1], v.x, v.y, acc0, acc1);
+                    fma2(acc0, acc1, Wd[4 * r4 + 2], Wd[4 * r4 + 3], v.z, v.w, acc0, acc1);
                 }
-                down[m] = okk ? softplus_f(acc0 + acc1) : 0.f;
+                const float sp = softplus_f(acc0 + acc1);
+                down[m] = okk ? sp : 0.f;
             }
             float dl[4], du[4], y[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 dl[i] = S == 1 ? down[i / S] : __shfl_sync(0xffffffffu, down[i / S], lane_base + (i % S));
                 du[i] = dl[i] * uu[i];
-                y[i] = 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4* bp = reinterpret_cast<const float4*>(ps + slot[i] * CP) + q;
                 const float4* cp = bp + 4;
+                float ye = 0.f, yo = 0.f;
 #pragma unroll
                 for (int j4 = 0; j4 < NS / 4; ++j4) {
                     const float4 bv = bp[j4 * S], cv = cp[j4 * S];
-                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = j4 * 4 + e;
-                        const float a = ex2_approx(dl[i] * Ap[j]);
-                        h[j] = fmaf(a, h[j], du[i] * bb[e]);
-                        y[i] = fmaf(h[j], cc[e], y[i]);
-                    }
+                    const int j = j4 * 4;
+                    float x0, x1, x2, x3, w0, w1, w2, w3;
+                    mul2(x0, x1, dl[i], dl[i], Ap[j + 0], Ap[j + 1]);
+                    mul2(x2, x3, dl[i], dl[i], Ap[j + 2], Ap[j + 3]);
+                    mul2(w0, w1, du[i], du[i], bv.x, bv.y);
+                    mul2(w2, w3, du[i], du[i], bv.z, bv.w);
+                    const float a0 = ex2_approx(x0), a1 = ex2_approx(x1), a2 = ex2_approx(x2), a3 = ex2_approx(x3);
+                    fma2(h[j + 0], h[j + 1], a0, a1, h[j + 0], h[j + 1], w0, w1);
+                    fma2(h[j + 2], h[j + 3], a2, a3, h[j + 2], h[j + 3], w2, w3);
+                    fma2(ye, yo, h[j + 0], h[j + 1], cv.x, cv.y, ye, yo);
+                    fma2(ye, yo, h[j + 2], h[j + 3], cv.z, cv.w, ye, yo);
                 }
+                y[i] = ye + yo;
             }
 #pragma unroll
             for (int off = S / 2; off > 0; off >>= 1) {
@@ -212,9 +221,12 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (ok[i] && cvalid && q == (i % S) && !(p.dbg & 2)) yb[pos[i] * ystride] = fmaf(Dd, uu[i], y[i]);
+                if (ok[i] && cvalid && q == (i % S)) yb[pos[i] * ystride] = fmaf(Dd, uu[i], y[i]);
             }
-        }
+        };
+        const int nfull = nsteps & ~3;
+        for (int g0 = 0; g0 < nfull; g0 += 4) group(std::true_type{}, g0);
+        if (nfull < nsteps) group(std::false_type{}, nfull);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -293,6 +305,7 @@ static int launch_core(const CorePlan& pl, const CoreFwdParams& p, const float* 
     auto kern = ss2d_core_fwd_kernel<S, RP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_status(e);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(pl.tiles, 4, p.B);
     kern<<<grid, pl.threads, pl.smem, st>>>(tmx_row, tmx_col, tmp_row, tmp_col, p);
     return launch_status();
