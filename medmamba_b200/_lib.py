@@ -84,3 +84,62 @@ def require_cuda(*tensors) -> torch.device:
         elif t.device != dev:
             raise RuntimeError("all tensors must be on the same CUDA device")
     return dev
+
+
+# ------------------------------------------------------------------------ launch accounting
+class KernelTimer:
+    """Counts the launches of this library's kernels and, with CUDA events recorded on the launch
+    stream either side of each one, their device time (bench.py's live roofline measurement)."""
+
+    def __init__(self, timing: bool = True):
+        self.timing = timing
+        self.launches = 0
+        self._events = []
+
+    def add(self, key, start, end):
+        self._events.append((key, start, end))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for key, a, b in self._events:
+            d = out.setdefault(key, {"count": 0, "total_ms": 0.0})
+            d["count"] += 1
+            d["total_ms"] += a.elapsed_time(b)
+        for d in out.values():
+            d["avg_ms"] = d["total_ms"] / d["count"]
+        return out
+
+
+_timer = None
+
+
+def set_kernel_timer(timer) -> None:
+    global _timer
+    _timer = timer
+
+
+class timed_launch:
+    """with timed_launch("kernel", "shape key"): <one C-ABI call that launches one kernel>"""
+
+    __slots__ = ("key", "start")
+
+    def __init__(self, name: str, shape: str = ""):
+        self.key = f"{name}[{shape}]" if shape else name
+        self.start = None
+
+    def __enter__(self):
+        t = _timer
+        if t is not None:
+            t.launches += 1
+            if t.timing:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None and _timer is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _timer.add(self.key, self.start, end)
+        return False

@@ -237,7 +237,9 @@ struct CorePlan {
     size_t smem;
 };
 
-static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
+// Lanes per channel (S) and channels per CTA (CT): enough warps to fill the machine, CTAs of at
+// most 384 threads, TMA boxes of at most 256 channels.
+static bool plan_core_tiles(int B, int D, CorePlan& pl) {
     const long rows = 4L * B * D;
     const long want = 32L * 12 * num_sms();
     int S = 1;
@@ -250,11 +252,27 @@ static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
     int CT = (D + tiles - 1) / tiles;
     CT = (CT + gran - 1) / gran * gran;
     tiles = (D + CT - 1) / CT;
+    if (CT > 256) return false;
+    pl.S = S; pl.CT = CT; pl.tiles = tiles; pl.threads = CT * S;
+    return true;
+}
+
+// Steps per stage (cap) and the block geometry of both views.  The ring is sized so that shared
+// memory allows as many CTAs per SM as the register file does (regs = registers per thread of the
+// instantiated kernel): the kernel lives on warps in flight, not on deep prefetch.
+static bool plan_core_blocks(int H, int W, int RP, int regs, CorePlan& pl) {
     const int CP = 32 + RP;
-    int cap = kCoreStageBytes / ((CT + CP) * 4);
+    const int step_bytes = (pl.CT + CP) * 4;
+    const int regs_alloc = (regs + 7) / 8 * 8;
+    int ctas = 65536 / (pl.threads * regs_alloc);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 16) ctas = 16;
+    int stage_bytes = (220 * 1024 / ctas - 1024) / kCoreStages;
+    if (stage_bytes > kCoreStageBytes) stage_bytes = kCoreStageBytes;
+    int cap = stage_bytes / step_bytes;
     if (cap > 32) cap = 32;
-    if (const char* e = getenv("MMB_CORE_CAP")) { const int v = atoi(e); if (v >= 4 && v <= 32 && v < cap) cap = v; }
-    if (cap < 4) return false;
+    if (cap < 8) cap = 8;
+    if (const char* e = getenv("MMB_CORE_CAP")) { const int v = atoi(e); if (v >= 4 && v <= 32) cap = v; }
     const int L = H * W;
     pl.NB_row = (L + cap - 1) / cap;
     pl.T_row = (L + pl.NB_row - 1) / pl.NB_row;
@@ -268,18 +286,27 @@ static bool plan_core(int B, int H, int W, int D, int RP, CorePlan& pl) {
         pl.NI_col = (H + cap - 1) / cap;
         pl.T_col = (H + pl.NI_col - 1) / pl.NI_col;
     }
-    if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256 || CT > 256) return false;
+    if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256) return false;
     pl.cap = pl.T_row > pl.nw * pl.T_col ? pl.T_row : pl.nw * pl.T_col;
-    pl.S = S; pl.CT = CT; pl.tiles = tiles;
-    pl.threads = CT * S;
-    const size_t xpad = ((size_t)pl.cap * CT * 4 + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
+    const size_t xpad = ((size_t)pl.cap * pl.CT * 4 + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
     pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
-    return true;
+    return pl.smem <= 200 * 1024;
 }
 
 template <int S, int RP>
-static int launch_core(const CorePlan& pl, const CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+static int launch_core(CorePlan& pl, CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
     constexpr int CP = 32 + RP;
+    auto kern = ss2d_core_fwd_kernel<S, RP>;
+    static int regs = 0;
+    if (regs == 0) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return cuda_status(e);
+        regs = fa.numRegs;
+    }
+    if (!plan_core_blocks(p.H, p.W, RP, regs, pl)) return MMB_ERR_UNSUPPORTED;
+    p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
+    p.cap = pl.cap;
     CUtensorMap tmx_row, tmx_col, tmp_row, tmp_col;
     const uint64_t B = p.B, H = p.H, W = p.W, L = p.L, D = p.D;
     {
@@ -302,7 +329,6 @@ static int launch_core(const CorePlan& pl, const CoreFwdParams& p, const float* 
         const uint32_t box[5] = {CP, 1, (uint32_t)pl.nw, (uint32_t)pl.T_col, 1};
         if (!make_tmap(&tmp_col, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, proj, dims, str, box)) return MMB_ERR_UNSUPPORTED;
     }
-    auto kern = ss2d_core_fwd_kernel<S, RP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return cuda_status(e);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -312,7 +338,7 @@ static int launch_core(const CorePlan& pl, const CoreFwdParams& p, const float* 
 }
 
 template <int RP>
-static int dispatch_core_s(const CorePlan& pl, const CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+static int dispatch_core_s(CorePlan& pl, CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
     switch (pl.S) {
         case 1: return launch_core<1, RP>(pl, p, xc, proj, st);
         case 2: return launch_core<2, RP>(pl, p, xc, proj, st);
@@ -339,12 +365,10 @@ extern "C" int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float
     if ((reinterpret_cast<uintptr_t>(xc) | reinterpret_cast<uintptr_t>(proj)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     CorePlan pl;
-    if (!plan_core(batch, H, W, D, dt_pad, pl)) return MMB_ERR_UNSUPPORTED;
+    if (!plan_core_tiles(batch, D, pl)) return MMB_ERR_UNSUPPORTED;
     CoreFwdParams p;
     p.ydir = ydir; p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds;
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank; p.CT = pl.CT;
-    p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
-    p.cap = pl.cap;
     p.kmask = 15;
     if (const char* e = getenv("MMB_CORE_KMASK")) p.kmask = atoi(e);
     p.dbg = 0;

@@ -10,7 +10,7 @@ import ctypes
 import torch
 import torch.nn.functional as F
 
-from ._lib import check, dtype_code, i64, lib, ptr, require_cuda, stream_ptr
+from ._lib import KernelTimer, check, dtype_code, i64, lib, ptr, require_cuda, set_kernel_timer, stream_ptr, timed_launch  # noqa: F401
 
 _c_int = ctypes.c_int
 
@@ -57,7 +57,7 @@ def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
     out = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
     w = weight.detach().float().contiguous()
     bs = bias.detach().float().contiguous() if bias is not None else None
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), timed_launch("dwconv3x3_silu_fwd", f"B={B},L={H * W},D={D}"):
         st = lib().mmb_dwconv3x3_silu_fwd(ptr(x), ptr(w), ptr(bs), ptr(out), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
                                           i64(x.stride(2)), i64(x.stride(0)), _c_int(dtype_code(x)),
                                           _c_int(dtype_code(out)), stream_ptr(dev))
@@ -72,7 +72,7 @@ def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int) -> torc
     rp = dt_pad(dt_rank)
     assert proj.shape == (B, H, W, 4, 32 + rp) and proj.is_contiguous() and xc.is_contiguous()
     ydir = torch.empty((B, H, W, 4, D), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), timed_launch("ss2d_core_fwd", f"B={B},L={H * W},D={D},R={dt_rank}"):
         st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir),
                                      _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
                                      _c_int(rp), stream_ptr(dev))
@@ -90,7 +90,7 @@ def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
     merged = torch.empty((B, H, W, D), dtype=torch.float32, device=dev) if want_merged else None
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), timed_launch("outnorm_gate_fwd", f"B={B},L={H * W},D={D}"):
         st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged), i64(B * H * W),
                                         _c_int(D), i64(z.stride(2)), ctypes.c_float(eps), _c_int(dtype_code(z)),
                                         _c_int(dtype_code(out)), stream_ptr(dev))
@@ -115,7 +115,7 @@ def shuffle_cat_residual_raw(left, ssm, inp) -> torch.Tensor:
     ssm, sp = _token_view(ssm.to(dt))
     inp, ip = _token_view(inp)
     out = torch.empty((B, H, W, 2 * c), dtype=dt, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), timed_launch("shuffle_cat_residual_fwd", f"B={B},L={H * W},c={c}"):
         st = lib().mmb_shuffle_cat_residual_fwd(ptr(left), ptr(ssm), ptr(inp), ptr(out), i64(B * H * W), _c_int(c),
                                                 i64(lp), i64(sp), i64(ip), _c_int(dtype_code(inp)), stream_ptr(dev))
     check(st, "mmb_shuffle_cat_residual_fwd")

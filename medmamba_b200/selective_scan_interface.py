@@ -18,7 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import check, dtype_code, i64, lib, ptr, require_cuda, stream_ptr
+from ._lib import check, dtype_code, i64, lib, ptr, require_cuda, stream_ptr, timed_launch
 
 MAX_DSTATE = 16
 
@@ -99,7 +99,7 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
             last.zero_()
         return out, last, chunk_state
     zs = (z.stride(0), z.stride(1)) if z is not None else (0, 0)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), timed_launch("scan_fwd", f"B={batch},KD={dim},L={L}"):
         st = lib().mmb_scan_fwd(
             ptr(u), ptr(delta), ptr(A), ptr(B), ptr(C), ptr(D), ptr(z), ptr(delta_bias), ptr(out),
             ptr(last), ptr(chunk_state),
