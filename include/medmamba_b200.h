@@ -40,10 +40,10 @@ int mmb_abi_version(void);
 /* Static description of a status code (host only). */
 const char* mmb_status_string(int status);
 
-/* Length of the L-chunks mmb_scan_fwd checkpoints the state at (host only).  The optional
- * `chunk_state` buffer of mmb_scan_fwd holds ceil(seqlen / chunk) * dim * dstate floats per
- * batch element. */
-int mmb_scan_chunk_len(int batch, int dim, int seqlen);
+/* Spacing (in steps) of the state checkpoints mmb_scan_fwd writes and mmb_scan_bwd recomputes from
+ * (host only).  The `chunk_state` buffer holds ceil(seqlen / chunk) * dim * dstate floats per batch
+ * element. */
+int mmb_scan_chunk_len(void);
 
 /* selective_scan_fn forward -- replaces selective_scan_cuda.fwd reached from MedMamba.py:273-279
  * (semantics: temp.py:57-139).
@@ -67,6 +67,30 @@ int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* B
                  int64_t C_bs, int64_t C_gs, int64_t C_ns, int64_t C_ls,
                  int delta_softplus, int io_dtype, int bc_dtype, void* stream);
 
+/* Row tiles mmb_scan_bwd splits a B/C group into (host only): the leading extent of dB_part / dC_part. */
+int mmb_scan_bwd_row_tiles(int dim, int ngroups);
+
+/* selective_scan_fn backward -- replaces selective_scan_cuda.bwd behind loss.backward() (train.py:284);
+ * formulas: SURVEY.md Appendix B.  Inputs as mmb_scan_fwd plus
+ *   dout        : (batch, dim, seqlen) gradient of out, dtype io_dtype, strides dout_bs / dout_ds
+ *   chunk_state : the checkpoints the forward wrote (may be NULL when seqlen <= mmb_scan_chunk_len())
+ * Outputs (all overwritten, no accumulation, no atomics):
+ *   du, ddelta, dz : (batch, dim, seqlen) dense, dtype io_dtype (ddelta is w.r.t. the RAW delta input;
+ *                    dz only when z != NULL)
+ *   dB_part, dC_part : (row_tiles, batch, ngroups, dstate, seqlen) fp32 -- sum over axis 0 = dB, dC
+ *   dA_part : (batch, dim, dstate) fp32;  dD_part, dbias_part : (batch, dim) fp32 -- sum over axis 0
+ * dstate <= 16. */
+int mmb_scan_bwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
+                 const float* Dv, const void* z, const float* delta_bias, const void* dout,
+                 const float* chunk_state, void* du, void* ddelta, void* dz,
+                 float* dB_part, float* dC_part, float* dA_part, float* dD_part, float* dbias_part,
+                 int batch, int dim, int seqlen, int dstate, int ngroups,
+                 int64_t u_bs, int64_t u_ds, int64_t delta_bs, int64_t delta_ds,
+                 int64_t z_bs, int64_t z_ds, int64_t dout_bs, int64_t dout_ds,
+                 int64_t B_bs, int64_t B_gs, int64_t B_ns, int64_t B_ls,
+                 int64_t C_bs, int64_t C_gs, int64_t C_ns, int64_t C_ls,
+                 int delta_softplus, int io_dtype, int bc_dtype, void* stream);
+
 /* ---- fused SS2D path (channels-last; every tensor is indexed by token position p = h*W + w) ---- */
 
 /* Depthwise 3x3 conv (padding 1) + bias + SiLU on a channels-last view.  Replaces the NHWC->NCHW
@@ -74,7 +98,7 @@ int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* B
  *   x      : (batch, H, W, D) view, channel stride 1, pixel stride x_pixel_stride, batch stride
  *            x_batch_stride (elements) -- the first half of the in_proj output has pitch 2*D
  *   weight : (D, 1, 3, 3) fp32 contiguous;  bias: (D) fp32 or NULL
- *   out    : (batch, H, W, D) dense, dtype out_dtype (MMB_F32)
+ *   out    : (batch, H, W, D) dense, dtype out_dtype (MMB_F32 or MMB_BF16)
  * D % 4 == 0. */
 int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const float* bias, void* out,
                            int batch, int H, int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride,
@@ -88,15 +112,17 @@ int mmb_ss2d_core_dt_pad(int dt_rank);
  * (MedMamba.py:256-257), the dt_proj einsum and its copy (:262, :266), selective_scan_fn (:273-279,
  * delta_softplus=True, delta_bias=dt_projs_bias, z=None) and the flips / transposes of the
  * cross-merge (:282-286).
- *   xc    : (batch, H, W, D) fp32 dense        -- u of all four directions
+ *   xc    : (batch, H, W, D) dense, xc_dtype MMB_F32 or MMB_BF16 -- u of all four directions
  *   proj  : (batch, H, W, 4, 32 + dt_pad) fp32 -- per direction k the x_proj of the token:
  *           [0,16) = B_n, [16,32) = C_n (rows n >= dstate zero), [32, 32+dt_rank) = dt_r, rest zero
  *   Wdt   : (4, D, dt_rank)   dt_bias: (4, D)   A: (4*D, dstate) (= -exp(A_logs))   Ds: (4*D)
  *   ydir  : (batch, H, W, 4, D) fp32 -- direction k's scan output stored at the token it belongs to
- * Direction order and index maps: SURVEY.md Appendix A.  D % 4 == 0, dstate <= 16, dt_rank <= 32. */
-int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float* Wdt, const float* dt_bias,
+ * Direction order and index maps: SURVEY.md Appendix A.  D % 4 == 0 (fp32 xc) or D % 8 == 0 (bf16 xc),
+ * dstate <= 16, dt_rank <= 32. */
+int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
                       const float* A, const float* Ds, float* ydir,
-                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, void* stream);
+                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
+                      void* stream);
 
 /* y = ((y0 + y2) + y1) + y3 over ydir's direction slices (the operand order of MedMamba.py:298),
  * LayerNorm over D (MedMamba.py:300, eps as given) and * SiLU(z) (MedMamba.py:301).
@@ -109,12 +135,13 @@ int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const float* gamma, c
 
 /* out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
  * -- torch.cat + channel_shuffle(groups=2) + residual of MedMamba.py:355-357 (:308-320).
- *   left, ssm : (tokens, c) views, channel stride 1;  inp: (tokens, 2c) view;  out: (tokens, 2c) dense
- * c % 4 == 0. */
+ *   left, ssm : (tokens, c) views, channel stride 1, dtype branch_dtype
+ *   inp       : (tokens, 2c) view, dtype res_dtype;  out: (tokens, 2c) dense, dtype res_dtype
+ * c % 4 == 0.  branch_dtype == res_dtype, or 16-bit branches onto an fp32 residual stream (autocast). */
 int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* inp, void* out,
                                  int64_t tokens, int c, int64_t left_pixel_stride,
-                                 int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int dtype,
-                                 void* stream);
+                                 int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int branch_dtype,
+                                 int res_dtype, void* stream);
 
 #ifdef __cplusplus
 }

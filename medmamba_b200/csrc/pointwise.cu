@@ -134,9 +134,9 @@ outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, c
 // ------------------------------------------------------------------------------------------------
 // out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
 // (torch.cat + channel_shuffle(groups=2) + residual).  A thread produces 8 output channels.
-template <typename T>
+template <typename TB, typename T>   // TB: branch dtype (left, ssm); T: residual stream dtype (inp, out)
 __global__ void __launch_bounds__(256)
-shuffle_cat_residual_kernel(const T* __restrict__ left, const T* __restrict__ ssm, const T* __restrict__ inp,
+shuffle_cat_residual_kernel(const TB* __restrict__ left, const TB* __restrict__ ssm, const T* __restrict__ inp,
                             T* __restrict__ out, int64_t tokens, int c, int64_t left_pix, int64_t ssm_pix,
                             int64_t inp_pix) {
     const int C4 = c / 4;
@@ -144,8 +144,8 @@ shuffle_cat_residual_kernel(const T* __restrict__ left, const T* __restrict__ ss
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(idx % C4);
         const int64_t tok = idx / C4;
-        const float4 l = load4<T>(left + tok * left_pix + 4 * c4);
-        const float4 s = load4<T>(ssm + tok * ssm_pix + 4 * c4);
+        const float4 l = load4<TB>(left + tok * left_pix + 4 * c4);
+        const float4 s = load4<TB>(ssm + tok * ssm_pix + 4 * c4);
         const float4 i0 = load4<T>(inp + tok * inp_pix + 8 * c4);
         const float4 i1 = load4<T>(inp + tok * inp_pix + 8 * c4 + 4);
         float4 o0, o1;
@@ -191,6 +191,8 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
     if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_DW(float, float);
     if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_DW(__nv_bfloat16, float);
     if (in_dtype == MMB_F16 && out_dtype == MMB_F32) MMB_DW(__half, float);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16) MMB_DW(__nv_bfloat16, __nv_bfloat16);
+    if (in_dtype == MMB_F32 && out_dtype == MMB_BF16) MMB_DW(float, __nv_bfloat16);
 #undef MMB_DW
     return MMB_ERR_UNSUPPORTED;
 }
@@ -231,8 +233,8 @@ extern "C" int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const floa
 
 extern "C" int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* inp, void* out,
                                             int64_t tokens, int c, int64_t left_pixel_stride,
-                                            int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int dtype,
-                                            void* stream) {
+                                            int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int branch_dtype,
+                                            int res_dtype, void* stream) {
     using namespace mmb;
     if (!left || !ssm || !inp || !out) return MMB_ERR_INVALID_ARG;
     if (tokens < 0 || c <= 0) return MMB_ERR_INVALID_ARG;
@@ -241,18 +243,20 @@ extern "C" int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, c
     if (tokens == 0) return MMB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(tokens * (c / 4), 256);
-#define MMB_SH(T)                                                                                                \
+#define MMB_SH(TB, T)                                                                                            \
     do {                                                                                                         \
-        if (!aligned_for4<T>(left) || !aligned_for4<T>(ssm) || !aligned_for4<T>(inp) || !aligned_for4<T>(out))   \
+        if (!aligned_for4<TB>(left) || !aligned_for4<TB>(ssm) || !aligned_for4<T>(inp) || !aligned_for4<T>(out)) \
             return MMB_ERR_UNSUPPORTED;                                                                          \
-        shuffle_cat_residual_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(left),                   \
-            reinterpret_cast<const T*>(ssm), reinterpret_cast<const T*>(inp), reinterpret_cast<T*>(out), tokens, \
+        shuffle_cat_residual_kernel<TB, T><<<grid, 256, 0, st>>>(reinterpret_cast<const TB*>(left),              \
+            reinterpret_cast<const TB*>(ssm), reinterpret_cast<const T*>(inp), reinterpret_cast<T*>(out), tokens,\
             c, left_pixel_stride, ssm_pixel_stride, inp_pixel_stride);                                           \
         return launch_status();                                                                                  \
     } while (0)
-    if (dtype == MMB_F32) MMB_SH(float);
-    if (dtype == MMB_BF16) MMB_SH(__nv_bfloat16);
-    if (dtype == MMB_F16) MMB_SH(__half);
+    if (branch_dtype == MMB_F32 && res_dtype == MMB_F32) MMB_SH(float, float);
+    if (branch_dtype == MMB_BF16 && res_dtype == MMB_BF16) MMB_SH(__nv_bfloat16, __nv_bfloat16);
+    if (branch_dtype == MMB_F16 && res_dtype == MMB_F16) MMB_SH(__half, __half);
+    if (branch_dtype == MMB_BF16 && res_dtype == MMB_F32) MMB_SH(__nv_bfloat16, float);
+    if (branch_dtype == MMB_F16 && res_dtype == MMB_F32) MMB_SH(__half, float);
 #undef MMB_SH
     return MMB_ERR_UNSUPPORTED;
 }

@@ -262,6 +262,7 @@ static int launch_scan_fwd(const ScanFwdParams& p, cudaStream_t stream) {
 template <typename io_t, typename bc_t>
 static int dispatch_split(const ScanFwdParams& p, int S, cudaStream_t stream) {
     switch (S) {
+        case 0: return launch_scan_fwd<4, 16, io_t, bc_t>(p, stream);
         case 1: return launch_scan_fwd<1, 32, io_t, bc_t>(p, stream);
         case 2: return launch_scan_fwd<2, 64, io_t, bc_t>(p, stream);
         case 4: return launch_scan_fwd<4, 64, io_t, bc_t>(p, stream);
@@ -280,11 +281,8 @@ static int dispatch_bc(const ScanFwdParams& p, int io_dtype, int bc_dtype, int S
 
 }  // namespace mmb
 
-extern "C" int mmb_scan_chunk_len(int batch, int dim, int seqlen) {
-    (void)seqlen;
-    if (batch <= 0 || dim <= 0) return MMB_ERR_INVALID_ARG;
-    return mmb::chunk_for_split(mmb::pick_split(batch, dim));
-}
+// spacing of the state checkpoints written when chunk_state != NULL (= the backward's chunk)
+extern "C" int mmb_scan_chunk_len(void) { return 16; }
 
 extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
                             const float* Dv, const void* z, const float* delta_bias, void* out,
@@ -311,8 +309,9 @@ extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, co
     p.z_bs = z_bs; p.z_ds = z_ds; p.o_bs = out_bs; p.o_ds = out_ds;
     p.B_bs = B_bs; p.B_gs = B_gs; p.B_ns = B_ns; p.B_ls = B_ls;
     p.C_bs = C_bs; p.C_gs = C_gs; p.C_ns = C_ns; p.C_ls = C_ls;
-    const int S = pick_split(batch, dim);
-    const int T = chunk_for_split(S);
+    // with checkpoints: 4 lanes per row and 16-step chunks, the geometry mmb_scan_bwd recomputes from
+    const int S = chunk_state ? 0 : pick_split(batch, dim);
+    const int T = chunk_state ? 16 : chunk_for_split(S);
     p.nchunks = (seqlen + T - 1) / T;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (io_dtype) {

@@ -46,7 +46,7 @@ struct CoreFwdParams {
     int dbg;                           // debug flags: 1 = try_wait instead of polling
 };
 
-template <int S, int RP>
+template <int S, int RP, typename xc_t>
 __global__ void __launch_bounds__(384)
 ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
@@ -56,7 +56,8 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     constexpr int OWN = 4 / S;          // delta evaluations per lane per group of 4 steps
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int xbytes = p.cap * p.CT * 4, pbytes = p.cap * CP * 4;
+    constexpr int XE = (int)sizeof(xc_t);
+    const int xbytes = p.cap * p.CT * XE, pbytes = p.cap * CP * 4;
     const int xpad = (xbytes + 127) & ~127, ppad = (pbytes + 127) & ~127;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kCoreStages * (xpad + ppad));
     uint64_t* empty = full + kCoreStages;
@@ -75,12 +76,12 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         uint8_t* xs = smem_raw + s * (xpad + ppad);
         uint8_t* ps = xs + xpad;
         if (!colview) {
-            mbar_expect_tx(&full[s], p.T_row * (p.CT + CP) * 4);
+            mbar_expect_tx(&full[s], p.T_row * (p.CT * XE + CP * 4));
             tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
             tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
         } else {
             const int o = blk / p.NI_col, i = blk % p.NI_col;
-            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT + CP) * 4);
+            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * XE + CP * 4));
             tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
             tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
         }
@@ -144,7 +145,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             slot_l = hh * nwbox + ww;
             pos_l = pbase + hh * psh + ww;
         }
-        const float* xs = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad)) + cl;
+        const xc_t* xs = reinterpret_cast<const xc_t*>(smem_raw + s * (xpad + ppad)) + cl;
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
         if (p.dbg & 1) { while (!mbar_try_wait(&full[s], ph)) {} } else mbar_wait(&full[s], ph);
 
@@ -163,7 +164,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
             float uu[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? xs[slot[i] * p.CT] : 0.f;
+            for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? to_f<xc_t>(xs[slot[i] * p.CT]) : 0.f;
             // delta = softplus(Wdt . dt_r + bias): each lane evaluates OWN of the four steps
             float down[OWN];
 #pragma unroll
@@ -260,9 +261,9 @@ static bool plan_core_tiles(int B, int D, CorePlan& pl) {
 // Steps per stage (cap) and the block geometry of both views.  The ring is sized so that shared
 // memory allows as many CTAs per SM as the register file does (regs = registers per thread of the
 // instantiated kernel): the kernel lives on warps in flight, not on deep prefetch.
-static bool plan_core_blocks(int H, int W, int RP, int regs, CorePlan& pl) {
+static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, CorePlan& pl) {
     const int CP = 32 + RP;
-    const int step_bytes = (pl.CT + CP) * 4;
+    const int step_bytes = pl.CT * XE + CP * 4;
     const int regs_alloc = (regs + 7) / 8 * 8;
     int ctas = 65536 / (pl.threads * regs_alloc);
     if (ctas < 1) ctas = 1;
@@ -288,15 +289,17 @@ static bool plan_core_blocks(int H, int W, int RP, int regs, CorePlan& pl) {
     }
     if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256) return false;
     pl.cap = pl.T_row > pl.nw * pl.T_col ? pl.T_row : pl.nw * pl.T_col;
-    const size_t xpad = ((size_t)pl.cap * pl.CT * 4 + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
+    const size_t xpad = ((size_t)pl.cap * pl.CT * XE + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
     pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
     return pl.smem <= 200 * 1024;
 }
 
-template <int S, int RP>
-static int launch_core(CorePlan& pl, CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+template <int S, int RP, typename xc_t>
+static int launch_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
     constexpr int CP = 32 + RP;
-    auto kern = ss2d_core_fwd_kernel<S, RP>;
+    constexpr uint64_t XE = sizeof(xc_t);
+    const CUtensorMapDataType xdt = XE == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    auto kern = ss2d_core_fwd_kernel<S, RP, xc_t>;
     static int regs = 0;
     if (regs == 0) {
         cudaFuncAttributes fa;
@@ -304,20 +307,20 @@ static int launch_core(CorePlan& pl, CoreFwdParams& p, const float* xc, const fl
         if (e != cudaSuccess) return cuda_status(e);
         regs = fa.numRegs;
     }
-    if (!plan_core_blocks(p.H, p.W, RP, regs, pl)) return MMB_ERR_UNSUPPORTED;
+    if (!plan_core_blocks(p.H, p.W, RP, regs, (int)XE, pl)) return MMB_ERR_UNSUPPORTED;
     p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
     p.cap = pl.cap;
     CUtensorMap tmx_row, tmx_col, tmp_row, tmp_col;
     const uint64_t B = p.B, H = p.H, W = p.W, L = p.L, D = p.D;
     {
-        const uint64_t dims[3] = {D, L, B}, str[2] = {D * 4, L * D * 4};
+        const uint64_t dims[3] = {D, L, B}, str[2] = {D * XE, L * D * XE};
         const uint32_t box[3] = {(uint32_t)pl.CT, (uint32_t)pl.T_row, 1};
-        if (!make_tmap(&tmx_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+        if (!make_tmap(&tmx_row, xdt, 3, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
     }
     {
-        const uint64_t dims[4] = {D, W, H, B}, str[3] = {D * 4, W * D * 4, L * D * 4};
+        const uint64_t dims[4] = {D, W, H, B}, str[3] = {D * XE, W * D * XE, L * D * XE};
         const uint32_t box[4] = {(uint32_t)pl.CT, (uint32_t)pl.nw, (uint32_t)pl.T_col, 1};
-        if (!make_tmap(&tmx_col, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
+        if (!make_tmap(&tmx_col, xdt, 4, xc, dims, str, box)) return MMB_ERR_UNSUPPORTED;
     }
     {
         const uint64_t dims[4] = {CP, 4, L, B}, str[3] = {CP * 4, 4 * CP * 4, L * 4 * CP * 4};
@@ -337,12 +340,25 @@ static int launch_core(CorePlan& pl, CoreFwdParams& p, const float* xc, const fl
     return launch_status();
 }
 
-template <int RP>
-static int dispatch_core_s(CorePlan& pl, CoreFwdParams& p, const float* xc, const float* proj, cudaStream_t st) {
+template <int RP, typename xc_t>
+static int dispatch_core_s(CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
     switch (pl.S) {
-        case 1: return launch_core<1, RP>(pl, p, xc, proj, st);
-        case 2: return launch_core<2, RP>(pl, p, xc, proj, st);
-        default: return launch_core<4, RP>(pl, p, xc, proj, st);
+        case 1: return launch_core<1, RP, xc_t>(pl, p, xc, proj, st);
+        case 2: return launch_core<2, RP, xc_t>(pl, p, xc, proj, st);
+        default: return launch_core<4, RP, xc_t>(pl, p, xc, proj, st);
+    }
+}
+
+template <typename xc_t>
+static int dispatch_core_rp(int dt_pad, CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
+    switch (dt_pad) {
+        case 4: return dispatch_core_s<4, xc_t>(pl, p, xc, proj, st);
+        case 8: return dispatch_core_s<8, xc_t>(pl, p, xc, proj, st);
+        case 12: return dispatch_core_s<12, xc_t>(pl, p, xc, proj, st);
+        case 16: return dispatch_core_s<16, xc_t>(pl, p, xc, proj, st);
+        case 24: return dispatch_core_s<24, xc_t>(pl, p, xc, proj, st);
+        case 32: return dispatch_core_s<32, xc_t>(pl, p, xc, proj, st);
+        default: return MMB_ERR_UNSUPPORTED;
     }
 }
 
@@ -354,14 +370,15 @@ extern "C" int mmb_ss2d_core_dt_pad(int dt_rank) {
     return MMB_ERR_UNSUPPORTED;
 }
 
-extern "C" int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float* Wdt, const float* dt_bias,
+extern "C" int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
                                  const float* A, const float* Ds, float* ydir,
-                                 int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, void* stream) {
+                                 int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype, void* stream) {
     using namespace mmb;
     if (!xc || !proj || !Wdt || !dt_bias || !A || !Ds || !ydir) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0 || dstate <= 0 || dt_rank <= 0) return MMB_ERR_INVALID_ARG;
     if (dstate > kMaxState || dt_pad != mmb_ss2d_core_dt_pad(dt_rank)) return MMB_ERR_UNSUPPORTED;
-    if (D % 4 != 0 || batch > 65535) return MMB_ERR_UNSUPPORTED;
+    if (xc_dtype != MMB_F32 && xc_dtype != MMB_BF16) return MMB_ERR_UNSUPPORTED;
+    if (D % (xc_dtype == MMB_F32 ? 4 : 8) != 0 || batch > 65535) return MMB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(xc) | reinterpret_cast<uintptr_t>(proj)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     CorePlan pl;
@@ -374,13 +391,6 @@ extern "C" int mmb_ss2d_core_fwd(const float* xc, const float* proj, const float
     p.dbg = 0;
     if (const char* e = getenv("MMB_CORE_DBG")) p.dbg = atoi(e);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (dt_pad) {
-        case 4: return dispatch_core_s<4>(pl, p, xc, proj, st);
-        case 8: return dispatch_core_s<8>(pl, p, xc, proj, st);
-        case 12: return dispatch_core_s<12>(pl, p, xc, proj, st);
-        case 16: return dispatch_core_s<16>(pl, p, xc, proj, st);
-        case 24: return dispatch_core_s<24>(pl, p, xc, proj, st);
-        case 32: return dispatch_core_s<32>(pl, p, xc, proj, st);
-        default: return MMB_ERR_UNSUPPORTED;
-    }
+    if (xc_dtype == MMB_F32) return dispatch_core_rp<float>(dt_pad, pl, p, xc, proj, st);
+    return dispatch_core_rp<__nv_bfloat16>(dt_pad, pl, p, xc, proj, st);
 }

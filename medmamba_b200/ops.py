@@ -48,13 +48,13 @@ def dt_pad(dt_rank: int) -> int:
     return rp
 
 
-def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
-    """x: (B, H, W, D) channels-last view (channel stride 1, uniform pixel pitch) -> dense fp32."""
+def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=torch.float32) -> torch.Tensor:
+    """x: (B, H, W, D) channels-last view (channel stride 1, uniform pixel pitch) -> dense (B, H, W, D)."""
     dev = require_cuda(x, weight, bias)
     B, H, W, D = x.shape
     if x.stride(3) != 1 or x.stride(1) != W * x.stride(2):
         x = x.contiguous()
-    out = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+    out = torch.empty((B, H, W, D), dtype=out_dtype, device=dev)
     w = weight.detach().float().contiguous()
     bs = bias.detach().float().contiguous() if bias is not None else None
     with torch.cuda.device(dev), timed_launch("dwconv3x3_silu_fwd", f"B={B},L={H * W},D={D}"):
@@ -66,7 +66,7 @@ def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
 
 
 def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int) -> torch.Tensor:
-    """xc (B, H, W, D) fp32, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) fp32."""
+    """xc (B, H, W, D) fp32 or bf16, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) fp32."""
     dev = require_cuda(xc, proj, Wdt, dt_bias, A, Ds)
     B, H, W, D = xc.shape
     rp = dt_pad(dt_rank)
@@ -75,7 +75,7 @@ def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int) -> torc
     with torch.cuda.device(dev), timed_launch("ss2d_core_fwd", f"B={B},L={H * W},D={D},R={dt_rank}"):
         st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir),
                                      _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
-                                     _c_int(rp), stream_ptr(dev))
+                                     _c_int(rp), _c_int(dtype_code(xc)), stream_ptr(dev))
     check(st, "mmb_ss2d_core_fwd")
     return ydir
 
@@ -111,13 +111,17 @@ def shuffle_cat_residual_raw(left, ssm, inp) -> torch.Tensor:
     dev = require_cuda(left, ssm, inp)
     B, H, W, c = ssm.shape
     dt = inp.dtype
-    left, lp = _token_view(left.to(dt))
-    ssm, sp = _token_view(ssm.to(dt))
+    bdt = ssm.dtype
+    if not (bdt == dt or (dt == torch.float32 and bdt in (torch.bfloat16, torch.float16))):
+        bdt = dt
+    left, lp = _token_view(left.to(bdt))
+    ssm, sp = _token_view(ssm.to(bdt))
     inp, ip = _token_view(inp)
     out = torch.empty((B, H, W, 2 * c), dtype=dt, device=dev)
     with torch.cuda.device(dev), timed_launch("shuffle_cat_residual_fwd", f"B={B},L={H * W},c={c}"):
         st = lib().mmb_shuffle_cat_residual_fwd(ptr(left), ptr(ssm), ptr(inp), ptr(out), i64(B * H * W), _c_int(c),
-                                                i64(lp), i64(sp), i64(ip), _c_int(dtype_code(inp)), stream_ptr(dev))
+                                                i64(lp), i64(sp), i64(ip), _c_int(dtype_code(ssm)), _c_int(dtype_code(inp)),
+                                                stream_ptr(dev))
     check(st, "mmb_shuffle_cat_residual_fwd")
     return out
 
@@ -133,30 +137,47 @@ def pack_x_proj(x_proj_weight: torch.Tensor, d_state: int, dt_rank: int) -> torc
     return torch.cat((pad(w_B, 16), pad(w_C, 16), pad(w_dt, rp)), dim=1).reshape(K * (32 + rp), D)
 
 
-# ------------------------------------------------------------------------ composed forward (no autograd yet)
+# ------------------------------------------------------------------------ composed forward (inference)
 def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
                eps, d_state, dt_rank):
     """Everything between in_proj and out_proj of SS2D.forward (MedMamba.py:292-301).
     xz: (B, H, W, 2D) -> gated, normalised y (B, H, W, D) in xz.dtype."""
-    if torch.is_grad_enabled() and any(t.requires_grad for t in (xz, conv_w, x_proj_weight, dt_projs_weight,
-                                                                  dt_projs_bias, A_logs, Ds, norm_w, norm_b)):
-        from .fused_autograd import ss2d_inner_autograd
-        return ss2d_inner_autograd(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds,
-                                   norm_w, norm_b, eps, d_state, dt_rank)
     B, H, W, D2 = xz.shape
     D = D2 // 2
     x, z = xz[..., :D], xz[..., D:]
-    xc = dwconv3x3_silu(x, conv_w, conv_b)
     w_packed = pack_x_proj(x_proj_weight.float(), d_state, dt_rank)
-    proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+    if xz.dtype == torch.bfloat16 and D % 8 == 0:
+        # autocast: bf16 activations, tensor-core x_proj with fp32 accumulate AND fp32 output
+        xc = dwconv3x3_silu(x, conv_w, conv_b, out_dtype=torch.bfloat16)
+        proj = torch.mm(xc.view(-1, D), w_packed.to(torch.bfloat16).t(), out_dtype=torch.float32).view(B, H, W, 4, -1)
+    else:
+        xc = dwconv3x3_silu(x, conv_w, conv_b)
+        proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
     A = -torch.exp(A_logs.float())
     ydir = ss2d_core(xc, proj, dt_projs_weight.float().contiguous(), dt_projs_bias.float().contiguous(),
                      A.contiguous(), Ds.float().contiguous(), d_state, dt_rank)
     return outnorm_gate(ydir, z, norm_w, norm_b, eps)
 
 
+class _ShuffleCatResidual(torch.autograd.Function):
+    """The backward of an interleave + add is a de-interleave: plain strided views, no kernel needed."""
+
+    @staticmethod
+    def forward(ctx, left, ssm, inp):
+        ctx.dtypes = (left.dtype, ssm.dtype, inp.dtype)
+        return shuffle_cat_residual_raw(left, ssm, inp)
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, ds, di = ctx.dtypes
+        return g[..., 0::2].to(dl), g[..., 1::2].to(ds), g.to(di)
+
+
 def shuffle_cat_residual(left, ssm, inp):
     if torch.is_grad_enabled() and any(t.requires_grad for t in (left, ssm, inp)):
-        from .fused_autograd import shuffle_cat_residual_autograd
-        return shuffle_cat_residual_autograd(left, ssm, inp)
+        return _ShuffleCatResidual.apply(left, ssm, inp)
     return shuffle_cat_residual_raw(left, ssm, inp)
+
+
+def needs_autograd(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

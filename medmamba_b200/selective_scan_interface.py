@@ -64,8 +64,8 @@ def _check_shapes(u, delta, A, B, C, D, z, delta_bias):
     return batch, dim, L, N
 
 
-def scan_chunk_len(batch: int, dim: int, seqlen: int) -> int:
-    return lib().mmb_scan_chunk_len(ctypes.c_int(batch), ctypes.c_int(dim), ctypes.c_int(seqlen))
+def scan_chunk_len() -> int:
+    return lib().mmb_scan_chunk_len()
 
 
 def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
@@ -92,7 +92,7 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
     last = torch.empty((batch, dim, N), dtype=torch.float32, device=dev) if want_last_state else None
     chunk_state = None
     if want_chunk_state and batch > 0 and L > 0:
-        T = scan_chunk_len(batch, dim, L)
+        T = scan_chunk_len()
         chunk_state = torch.empty((batch, dim, (L + T - 1) // T, N), dtype=torch.float32, device=dev)
     if batch == 0 or L == 0:
         if last is not None:
@@ -112,6 +112,61 @@ def scan_forward(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softp
             stream_ptr(dev))
     check(st, "mmb_scan_fwd")
     return out, last, chunk_state
+
+
+def scan_backward(u, delta, A, B, C, D, z, delta_bias, delta_softplus, dout, chunk_state):
+    """Raw backward: (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dB/dC grouped (B, G, N, L) in B.dtype."""
+    dev = require_cuda(u, delta, A, B, C, D, z, delta_bias, dout)
+    Bg, Cg = _as_grouped(B, "B"), _as_grouped(C, "C")
+    batch, dim, L, N = _check_shapes(u, delta, A, Bg, Cg, D, z, delta_bias)
+    io = u.dtype
+    delta = delta.to(io) if delta.dtype != io else delta
+    z = z.to(io) if (z is not None and z.dtype != io) else z
+    dout = dout.to(io) if dout.dtype != io else dout
+    bc_in = Bg.dtype
+    if Cg.dtype != Bg.dtype:
+        Cg = Cg.to(Bg.dtype)
+    if Bg.dtype not in (torch.float32, io):
+        Bg, Cg = Bg.float(), Cg.float()
+    u, delta, dout = _rows_contiguous(u), _rows_contiguous(delta), _rows_contiguous(dout)
+    z = _rows_contiguous(z) if z is not None else None
+    A32 = A.float().contiguous()
+    D32 = D.float().contiguous() if D is not None else None
+    b32 = delta_bias.float().contiguous() if delta_bias is not None else None
+    G = Bg.shape[1]
+    f32 = dict(dtype=torch.float32, device=dev)
+    du = torch.empty((batch, dim, L), dtype=io, device=dev)
+    ddelta = torch.empty((batch, dim, L), dtype=io, device=dev)
+    dz = torch.empty((batch, dim, L), dtype=io, device=dev) if z is not None else None
+    tiles = lib().mmb_scan_bwd_row_tiles(ctypes.c_int(dim), ctypes.c_int(G))
+    dBp = torch.empty((tiles, batch, G, N, L), **f32)
+    dCp = torch.empty((tiles, batch, G, N, L), **f32)
+    dAp = torch.empty((batch, dim, N), **f32)
+    dDp = torch.empty((batch, dim), **f32)
+    dbp = torch.empty((batch, dim), **f32)
+    if batch > 0 and L > 0:
+        zs = (z.stride(0), z.stride(1)) if z is not None else (0, 0)
+        with torch.cuda.device(dev), timed_launch("scan_bwd", f"B={batch},KD={dim},L={L}"):
+            st = lib().mmb_scan_bwd(
+                ptr(u), ptr(delta), ptr(A32), ptr(Bg), ptr(Cg), ptr(D32), ptr(z), ptr(b32), ptr(dout), ptr(chunk_state),
+                ptr(du), ptr(ddelta), ptr(dz), ptr(dBp), ptr(dCp), ptr(dAp), ptr(dDp), ptr(dbp),
+                ctypes.c_int(batch), ctypes.c_int(dim), ctypes.c_int(L), ctypes.c_int(N), ctypes.c_int(G),
+                i64(u.stride(0)), i64(u.stride(1)), i64(delta.stride(0)), i64(delta.stride(1)),
+                i64(zs[0]), i64(zs[1]), i64(dout.stride(0)), i64(dout.stride(1)),
+                i64(Bg.stride(0)), i64(Bg.stride(1)), i64(Bg.stride(2)), i64(Bg.stride(3)),
+                i64(Cg.stride(0)), i64(Cg.stride(1)), i64(Cg.stride(2)), i64(Cg.stride(3)),
+                ctypes.c_int(int(bool(delta_softplus))), ctypes.c_int(dtype_code(u)), ctypes.c_int(dtype_code(Bg)),
+                stream_ptr(dev))
+        check(st, "mmb_scan_bwd")
+    else:
+        for t in (dBp, dCp, dAp, dDp, dbp):
+            t.zero_()
+    dB = (dBp[0] if tiles == 1 else dBp.sum(0)).to(bc_in)
+    dC = (dCp[0] if tiles == 1 else dCp.sum(0)).to(C.dtype)
+    dA = dAp.sum(0).to(A.dtype)
+    dD = dDp.sum(0).to(D.dtype) if D is not None else None
+    dbias = dbp.sum(0).to(delta_bias.dtype) if delta_bias is not None else None
+    return du, ddelta, dA, dB, dC, dD, dz, dbias
 
 
 class SelectiveScanFn(torch.autograd.Function):
@@ -137,7 +192,6 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *unused):
-        from .scan_backward import scan_backward
         u, delta, A, B, C, D, z, delta_bias, chunk_state = ctx.saved_tensors
         grads = scan_backward(u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, dout, chunk_state)
         du, ddelta, dA, dB, dC, dD, dz, dbias = grads

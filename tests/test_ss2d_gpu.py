@@ -161,3 +161,47 @@ def test_vssm_t_config1_logits_and_top1():
     print("config-1 max |dlogit|", (logits.cpu() - g["logits"]).abs().max().item())
     assert_close(logits, g["logits"], 1e-3, 1e-4, "config-1 logits")
     assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
+
+
+def test_shuffle_mixed_dtype_autocast():
+    """bf16 branches onto the fp32 residual stream (what autocast produces)."""
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    left, ssm, inp = torch.randn(2, 6, 5, 16, generator=g).bfloat16(), torch.randn(2, 6, 5, 16, generator=g).bfloat16(), torch.randn(2, 6, 5, 32, generator=g)
+    want = medmamba_ref.channel_shuffle(torch.cat((left.float(), ssm.float()), -1), 2) + inp
+    got = ops.shuffle_cat_residual(left.cuda(), ssm.cuda(), inp.cuda())
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("d_model,H,W", [(48, 56, 56), (96, 28, 28), (192, 14, 14), (384, 7, 7), (8, 5, 9)])
+def test_ss2d_bf16_autocast_vs_fp32_oracle(d_model, H, W):
+    """bf16 path (BASELINE configs 2-4): within 1e-2 of the fp32 oracle, relative to max |y|."""
+    import medmamba_b200 as mm
+    torch.manual_seed(d_model)
+    m = mm.SS2D(d_model=d_model).eval()
+    with torch.no_grad():
+        m.A_logs.add_(0.2 * torch.randn_like(m.A_logs))
+        m.x_proj_weight.mul_(3.0)
+    x = torch.randn(2, H, W, d_model)
+    with torch.no_grad():
+        want = medmamba_ref.ss2d_forward({k: v for k, v in m.state_dict().items()}, "", x, scan_fn=cscan_fn)
+        m = m.cuda()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = m(x.cuda())
+    assert got.dtype == torch.bfloat16
+    err = (got.float().cpu() - want).abs().max().item() / want.abs().max().item()
+    assert err < 1e-2, err
+
+
+def test_vssm_t_bf16_top1_matches():
+    import medmamba_b200 as mm
+    g = _load("vssm_t_config1.npz")
+    torch.manual_seed(int(g["weight_seed"]))
+    net = mm.medmamba_t(num_classes=6).cuda().eval()
+    torch.manual_seed(int(g["input_seed"]))
+    x = torch.randn(8, 3, 224, 224)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = net(x.cuda()).float().cpu()
+    rel = (logits - g["logits"]).abs().max().item() / g["logits"].abs().max().item()
+    print("bf16 config-1 rel err", rel)
+    assert rel < 2e-2
