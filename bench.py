@@ -254,6 +254,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[3]: data-parallel training step (CE loss + AdamW, train.py:187-192), batch B per GPU,
+    gradients averaged with NCCL all-reduces over flat buckets.  One JSON line, same contract."""
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import medmamba_b200 as mm
+    from medmamba_b200 import dist as mdist, ops
+    mdist.init_from_env("nccl")
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)                                   # identical replicas
+    net = mm.medmamba_t(NUM_CLASSES).to(dev).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    red = mdist.GradAllReducer(net.parameters())
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(B, 3, RES, RES, device=dev, generator=g)
+    y = torch.randint(0, NUM_CLASSES, (B,), device=dev, generator=g)
+    amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with amp:
+            loss = torch.nn.functional.cross_entropy(net(x).float(), y)
+        loss.backward()
+        red.reduce()
+        opt.step()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    timer = ops.KernelTimer(timing=False)
+    ops.set_kernel_timer(timer)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ops.set_kernel_timer(None)
+    clocks = sampler.stop() if sampler else None
+    ms = mdist.max_over_ranks([e0.elapsed_time(e1)], device=dev)[0]
+    if rank == 0:
+        print(json.dumps({
+            "metric": "MedMamba-T training images/sec at 224x224", "value": round(world * B * args.steps / (ms / 1e3), 1),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"MedMamba-T training step (CE + AdamW), batch {B}/GPU, {RES}x{RES} synthetic (BASELINE configs[3])",
+                       "global_batch": world * B, "parallelism": f"dp{world}, flat-bucket NCCL all-reduce"},
+            "gpu_launches": timer.launches, "clocks": clocks, "loss": round(float(loss), 4)}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,9 +322,12 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 
