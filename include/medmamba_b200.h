@@ -108,6 +108,9 @@ int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const float* bias
  * MMB_ERR_UNSUPPORTED when dt_rank > 32. */
 int mmb_ss2d_core_dt_pad(int dt_rank);
 
+/* Blocks per direction of the training geometry (host only): the third extent of `hsave`. */
+int mmb_ss2d_core_train_blocks(int H, int W);
+
 /* Four-direction selective scan of SS2D.forward_corev0 in one launch.  Replaces the cross-scan
  * (MedMamba.py:256-257), the dt_proj einsum and its copy (:262, :266), selective_scan_fn (:273-279,
  * delta_softplus=True, delta_bias=dt_projs_bias, z=None) and the flips / transposes of the
@@ -117,10 +120,12 @@ int mmb_ss2d_core_dt_pad(int dt_rank);
  *           [0,16) = B_n, [16,32) = C_n (rows n >= dstate zero), [32, 32+dt_rank) = dt_r, rest zero
  *   Wdt   : (4, D, dt_rank)   dt_bias: (4, D)   A: (4*D, dstate) (= -exp(A_logs))   Ds: (4*D)
  *   ydir  : (batch, H, W, 4, D) fp32 -- direction k's scan output stored at the token it belongs to
+ *   hsave : NULL (inference), or (batch, 4, mmb_ss2d_core_train_blocks(H, W), D, 16) fp32: the state after
+ *           every block of 8 steps, in each direction's own time order -- what mmb_ss2d_core_bwd recomputes from
  * Direction order and index maps: SURVEY.md Appendix A.  D % 4 == 0 (fp32 xc) or D % 8 == 0 (bf16 xc),
  * dstate <= 16, dt_rank <= 32. */
 int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
-                      const float* A, const float* Ds, float* ydir,
+                      const float* A, const float* Ds, float* ydir, float* hsave,
                       int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
                       void* stream);
 
@@ -142,6 +147,50 @@ int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* 
                                  int64_t tokens, int c, int64_t left_pixel_stride,
                                  int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int branch_dtype,
                                  int res_dtype, void* stream);
+
+/* ---- backward of the fused path (training; loss.backward(), train.py:284).  Parameter gradients come back
+ * as per-CTA / per-batch partials that the caller sums over the leading axis: no float atomics, results are
+ * bit-reproducible. ---- */
+
+/* Rows of the partial buffers of mmb_outnorm_gate_bwd and mmb_dwconv3x3_silu_bwd_ds (host only). */
+int mmb_partial_blocks(void);
+
+/* Channel tiles mmb_ss2d_core_bwd cuts D into (host only): leading extent of dBC_part. */
+int mmb_ss2d_core_bwd_tiles(int D);
+
+/* Gradient of mmb_ss2d_core_fwd given dY (batch, H, W, D) fp32 -- the gradient of the merged sum, identical for
+ * the four direction slices of ydir.  xc, proj, Wdt, dt_bias, A, Ds as in the forward; hsave as written by it.
+ *   dudir    : (batch, H, W, 4, D) fp32 -- d xc through direction k's `u` (sum over k = that part of d xc)
+ *   ddraw    : (batch, H, W, 4, D) fp32 -- d (Wdt . dt_r + dt_bias); the host derives d dt_r, dWdt, d dt_bias
+ *   dBC_part : (tiles, batch, H, W, 4, 32) fp32 -- [0,16) dB_n, [16,32) dC_n; sum over axis 0
+ *   dA_part  : (batch, 4*D, dstate) fp32;  dD_part: (batch, 4*D) fp32 -- sum over axis 0 */
+int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const float* Wdt,
+                      const float* dt_bias, const float* A, const float* Ds, const float* hsave,
+                      float* dudir, float* ddraw, float* dBC_part, float* dA_part, float* dD_part,
+                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
+                      void* stream);
+
+/* Backward of mmb_outnorm_gate_fwd: dout (tokens, D) dense in z_dtype, ymerged from the forward ->
+ *   dy (tokens, D) fp32, dz (tokens, D) dense in z_dtype,
+ *   dgb_part (mmb_partial_blocks(), 2, D) fp32: [.,0,:] dgamma, [.,1,:] dbeta partials. */
+int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, const void* z, const float* gamma,
+                         const float* beta, float* dy, void* dz, float* dgb_part, int64_t tokens, int D,
+                         int64_t z_pixel_stride, float eps, int z_dtype, void* stream);
+
+/* Backward of mmb_dwconv3x3_silu_fwd, step 1: ds = dxc * silu'(dwconv(x) + bias) (pre-activation recomputed),
+ *   ds (batch, H, W, D) fp32, dwb_part (mmb_partial_blocks(), D, 10) fp32: [., c, 0..8] dweight taps, [., c, 9] dbias. */
+int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, const float* bias, const float* dxc,
+                              float* ds, float* dwb_part, int batch, int H, int W, int D,
+                              int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype, void* stream);
+
+/* ... step 2: dx = ds correlated with the flipped 3x3 kernel; dx (batch, H, W, D) dense in out_dtype. */
+int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* dx, int batch, int H, int W, int D,
+                         int out_dtype, void* stream);
+
+/* Backward of mmb_shuffle_cat_residual_fwd w.r.t. the two branches (d inp = dout):
+ *   dleft[..., j] = dout[..., 2j], dssm[..., j] = dout[..., 2j+1]; dense (tokens, c) in branch_dtype. */
+int mmb_shuffle_cat_residual_bwd(const void* dout, void* dleft, void* dssm, int64_t tokens, int c,
+                                 int res_dtype, int branch_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ namespace mmb {
 // Depthwise 3x3, padding 1, + bias, SiLU.  x is a channels-last view with an arbitrary pixel pitch
 // (it is the first half of the in_proj output, pitch 2*D); out is dense (B, H, W, D).
 // A thread owns 4 channels and a strip of WS output pixels along w: 3 x (WS + 2) float4 loads.
-template <int WS, typename in_t, typename out_t>
+template <int WS, typename in_t, typename out_t, bool ACT = true, bool FLIP = false>
 __global__ void __launch_bounds__(256)
 dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                       out_t* __restrict__ out, int B, int H, int W, int D, int64_t x_pix, int64_t x_batch) {
@@ -29,7 +29,7 @@ dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
 #pragma unroll
-            for (int tp = 0; tp < 9; ++tp) wk[tp][e] = __ldg(wgt + (int64_t)(c + e) * 9 + tp);
+            for (int tp = 0; tp < 9; ++tp) wk[tp][e] = __ldg(wgt + (int64_t)(c + e) * 9 + (FLIP ? 8 - tp : tp));
         }
         float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
@@ -62,7 +62,8 @@ dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
             const int wx = w0 + i;
             if (wx < W) {
                 float4 o;
-                o.x = silu_f(acc[i][0]); o.y = silu_f(acc[i][1]); o.z = silu_f(acc[i][2]); o.w = silu_f(acc[i][3]);
+                if (ACT) { o.x = silu_f(acc[i][0]); o.y = silu_f(acc[i][1]); o.z = silu_f(acc[i][2]); o.w = silu_f(acc[i][3]); }
+                else { o.x = acc[i][0]; o.y = acc[i][1]; o.z = acc[i][2]; o.w = acc[i][3]; }
                 store4<out_t>(out + (((int64_t)b * H + h) * W + wx) * D + c, o);
             }
         }
@@ -194,6 +195,32 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
     if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16) MMB_DW(__nv_bfloat16, __nv_bfloat16);
     if (in_dtype == MMB_F32 && out_dtype == MMB_BF16) MMB_DW(float, __nv_bfloat16);
 #undef MMB_DW
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* dx, int batch, int H, int W, int D,
+                                    int out_dtype, void* stream) {
+    using namespace mmb;
+    if (!ds || !weight || !dx) return MMB_ERR_INVALID_ARG;
+    if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
+    if (D % 4 != 0 || !aligned_for4<float>(ds)) return MMB_ERR_UNSUPPORTED;
+    if (batch == 0) return MMB_OK;
+    constexpr int WS = 4;
+    const int64_t items = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 4);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(items, 256);
+    if (out_dtype == MMB_F32) {
+        if (!aligned_for4<float>(dx)) return MMB_ERR_UNSUPPORTED;
+        dwconv3x3_silu_kernel<WS, float, float, false, true><<<grid, 256, 0, st>>>(
+            ds, weight, nullptr, reinterpret_cast<float*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
+        return launch_status();
+    }
+    if (out_dtype == MMB_BF16) {
+        if (!aligned_for4<__nv_bfloat16>(dx)) return MMB_ERR_UNSUPPORTED;
+        dwconv3x3_silu_kernel<WS, float, __nv_bfloat16, false, true><<<grid, 256, 0, st>>>(
+            ds, weight, nullptr, reinterpret_cast<__nv_bfloat16*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
+        return launch_status();
+    }
     return MMB_ERR_UNSUPPORTED;
 }
 

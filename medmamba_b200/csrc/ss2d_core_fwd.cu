@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "core_geom.cuh"
 #include "tma.cuh"
 
 namespace mmb {
@@ -44,6 +45,8 @@ struct CoreFwdParams {
     int cap;                           // steps a stage can hold
     int kmask;                         // debug: directions to run (bit k); 15 in production
     int dbg;                           // debug flags: 1 = try_wait instead of polling
+    float* hsave;                      // NULL, or (B, 4, NBmax, D, 16): state after every block (training)
+    int NBmax;
 };
 
 template <int S, int RP, typename xc_t>
@@ -228,6 +231,12 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         const int nfull = nsteps & ~3;
         for (int g0 = 0; g0 < nfull; g0 += 4) group(std::true_type{}, g0);
         if (nfull < nsteps) group(std::false_type{}, nfull);
+        if (p.hsave && cvalid) {
+            float* hs = p.hsave + ((((int64_t)b * 4 + k) * p.NBmax + jb) * p.D + c) * kMaxState + 4 * q;
+#pragma unroll
+            for (int j4 = 0; j4 < NS / 4; ++j4)
+                *reinterpret_cast<float4*>(hs + 4 * S * j4) = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -261,7 +270,7 @@ static bool plan_core_tiles(int B, int D, CorePlan& pl) {
 // Steps per stage (cap) and the block geometry of both views.  The ring is sized so that shared
 // memory allows as many CTAs per SM as the register file does (regs = registers per thread of the
 // instantiated kernel): the kernel lives on warps in flight, not on deep prefetch.
-static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, CorePlan& pl) {
+static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, bool train, CorePlan& pl) {
     const int CP = 32 + RP;
     const int step_bytes = pl.CT * XE + CP * 4;
     const int regs_alloc = (regs + 7) / 8 * 8;
@@ -274,21 +283,11 @@ static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, CorePlan& p
     if (cap > 32) cap = 32;
     if (cap < 8) cap = 8;
     if (const char* e = getenv("MMB_CORE_CAP")) { const int v = atoi(e); if (v >= 4 && v <= 32) cap = v; }
-    const int L = H * W;
-    pl.NB_row = (L + cap - 1) / cap;
-    pl.T_row = (L + pl.NB_row - 1) / pl.NB_row;
-    if (H <= cap) {
-        const int maxw = cap / H;
-        pl.NO_col = (W + maxw - 1) / maxw;
-        pl.nw = (W + pl.NO_col - 1) / pl.NO_col;
-        pl.T_col = H; pl.NI_col = 1;
-    } else {
-        pl.nw = 1; pl.NO_col = W;
-        pl.NI_col = (H + cap - 1) / cap;
-        pl.T_col = (H + pl.NI_col - 1) / pl.NI_col;
-    }
-    if (pl.T_row > 256 || pl.T_col > 256 || pl.nw > 256) return false;
-    pl.cap = pl.T_row > pl.nw * pl.T_col ? pl.T_row : pl.nw * pl.T_col;
+    if (train) cap = kTrainCap;      // checkpoint spacing is part of the forward/backward contract
+    CoreGeom g;
+    if (!core_geometry(H, W, cap, g)) return false;
+    pl.T_row = g.T_row; pl.NB_row = g.NB_row; pl.nw = g.nw; pl.T_col = g.T_col; pl.NI_col = g.NI_col; pl.NO_col = g.NO_col;
+    pl.cap = g.cap;
     const size_t xpad = ((size_t)pl.cap * pl.CT * XE + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
     pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
     return pl.smem <= 200 * 1024;
@@ -307,7 +306,8 @@ static int launch_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const flo
         if (e != cudaSuccess) return cuda_status(e);
         regs = fa.numRegs;
     }
-    if (!plan_core_blocks(p.H, p.W, RP, regs, (int)XE, pl)) return MMB_ERR_UNSUPPORTED;
+    if (!plan_core_blocks(p.H, p.W, RP, regs, (int)XE, p.hsave != nullptr, pl)) return MMB_ERR_UNSUPPORTED;
+    if (p.hsave) { CoreGeom g; core_geometry(p.H, p.W, kTrainCap, g); p.NBmax = g.nblocks_max(); }
     p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
     p.cap = pl.cap;
     CUtensorMap tmx_row, tmx_col, tmp_row, tmp_col;
@@ -370,8 +370,15 @@ extern "C" int mmb_ss2d_core_dt_pad(int dt_rank) {
     return MMB_ERR_UNSUPPORTED;
 }
 
+extern "C" int mmb_ss2d_core_train_blocks(int H, int W) {
+    if (H <= 0 || W <= 0) return MMB_ERR_INVALID_ARG;
+    mmb::CoreGeom g;
+    if (!mmb::core_geometry(H, W, mmb::kTrainCap, g)) return MMB_ERR_UNSUPPORTED;
+    return g.nblocks_max();
+}
+
 extern "C" int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
-                                 const float* A, const float* Ds, float* ydir,
+                                 const float* A, const float* Ds, float* ydir, float* hsave,
                                  int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype, void* stream) {
     using namespace mmb;
     if (!xc || !proj || !Wdt || !dt_bias || !A || !Ds || !ydir) return MMB_ERR_INVALID_ARG;
@@ -384,7 +391,7 @@ extern "C" int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float*
     CorePlan pl;
     if (!plan_core_tiles(batch, D, pl)) return MMB_ERR_UNSUPPORTED;
     CoreFwdParams p;
-    p.ydir = ydir; p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds;
+    p.ydir = ydir; p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds; p.hsave = hsave; p.NBmax = 0;
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank; p.CT = pl.CT;
     p.kmask = 15;
     if (const char* e = getenv("MMB_CORE_KMASK")) p.kmask = atoi(e);

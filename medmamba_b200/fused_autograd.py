@@ -1,0 +1,172 @@
+"""Autograd for the fused SS2D path: every forward kernel of ``ops`` paired with its hand-written backward
+(``mmb_*_bwd`` in include/medmamba_b200.h).  Parameter gradients arrive as partial sums (per CTA / per batch
+element / per channel tile) and are added here with ``torch.sum`` -- deterministic, no atomics."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import check, dtype_code, i64, lib, ptr, stream_ptr, timed_launch
+
+_c_int = ctypes.c_int
+
+
+def _partial_blocks() -> int:
+    return lib().mmb_partial_blocks()
+
+
+class DwConvSiluFn(torch.autograd.Function):
+    """xc = silu(dwconv3x3(x) + bias), channels-last (MedMamba.py:294-295)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_dtype):
+        xc = ops.dwconv3x3_silu(x, weight, bias, out_dtype=out_dtype)
+        ctx.save_for_backward(x, weight, bias)
+        return xc
+
+    @staticmethod
+    def backward(ctx, dxc):
+        x, weight, bias = ctx.saved_tensors
+        B, H, W, D = x.shape
+        dev = x.device
+        xv, px, bs = ops._token_view(x, uniform_batch=False)
+        w = weight.detach().float().contiguous()
+        bb = bias.detach().float().contiguous() if bias is not None else None
+        g = dxc.float().contiguous()
+        ds = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+        part = torch.empty((_partial_blocks(), D, 10), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            with timed_launch("dwconv3x3_silu_bwd_ds", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), ptr(g), ptr(ds), ptr(part), _c_int(B),
+                                                     _c_int(H), _c_int(W), _c_int(D), i64(px), i64(bs),
+                                                     _c_int(dtype_code(xv)), stream_ptr(dev))
+            check(st, "mmb_dwconv3x3_silu_bwd_ds")
+            dx = torch.empty((B, H, W, D), dtype=x.dtype, device=dev)
+            with timed_launch("dwconv3x3_bwd_dx", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_dwconv3x3_bwd_dx(ptr(ds), ptr(w), ptr(dx), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
+                                                _c_int(dtype_code(dx)), stream_ptr(dev))
+            check(st, "mmb_dwconv3x3_bwd_dx")
+        tot = part.sum(0)                                   # (D, 10)
+        dw = tot[:, :9].reshape(D, 1, 3, 3).to(weight.dtype)
+        db = tot[:, 9].to(bias.dtype) if bias is not None else None
+        return dx, dw, db, None
+
+
+class _MmF32Out(torch.autograd.Function):
+    """bf16 x bf16 -> fp32 GEMM (tensor cores, fp32 accumulate AND output) with its two backward GEMMs."""
+
+    @staticmethod
+    def forward(ctx, a, w):                                  # a (M, K) bf16, w (Nout, K) fp32 parameter-side
+        wb = w.to(torch.bfloat16)
+        ctx.save_for_backward(a, wb)
+        ctx.w_dtype = w.dtype
+        return torch.mm(a, wb.t(), out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, wb = ctx.saved_tensors
+        gb = g.to(torch.bfloat16)
+        da = torch.mm(gb, wb)
+        dw = torch.mm(gb.t(), a, out_dtype=torch.float32).to(ctx.w_dtype)
+        return da, dw
+
+
+class CoreNormGateFn(torch.autograd.Function):
+    """(xc, proj, z, params) -> out_norm(sum of the four directional scans) * silu(z)
+    = MedMamba.py:256-286 (without x_proj) + :298-301, forward and backward in four kernels."""
+
+    @staticmethod
+    def forward(ctx, xc, proj, z, Wdt, dt_bias, A, Ds, gamma, beta, eps, d_state, dt_rank):
+        Wdt_c, b_c, A_c, D_c = (Wdt.float().contiguous(), dt_bias.float().contiguous(), A.float().contiguous(),
+                                Ds.float().contiguous())
+        ydir, hsave = ops.ss2d_core(xc, proj, Wdt_c, b_c, A_c, D_c, d_state, dt_rank, save_states=True)
+        y, merged = ops.outnorm_gate(ydir, z, gamma, beta, eps, want_merged=True)
+        ctx.save_for_backward(xc, proj, z, Wdt_c, b_c, A_c, D_c, gamma, beta, merged, hsave)
+        ctx.meta = (eps, d_state, dt_rank, Wdt.dtype, dt_bias.dtype, A.dtype, Ds.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, proj, z, Wdt, dt_bias, A, Ds, gamma, beta, merged, hsave = ctx.saved_tensors
+        eps, N, R, wdt_t, b_t, a_t, d_t = ctx.meta
+        B, H, W, D = xc.shape
+        dev = xc.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        rp = ops.dt_pad(R)
+        zv, z_px, _ = ops._token_view(z)
+        dout = dout.to(zv.dtype).contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        dy = torch.empty((B, H, W, D), **f32)
+        dz = torch.empty((B, H, W, D), dtype=zv.dtype, device=dev)
+        gb_part = torch.empty((_partial_blocks(), 2, D), **f32)
+        tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(D))
+        dudir = torch.empty((B, H, W, 4, D), **f32)
+        ddraw = torch.empty((B, H, W, 4, D), **f32)
+        dBC = torch.empty((tiles, B, H, W, 4, 32), **f32)
+        dA_p = torch.empty((B, 4 * D, N), **f32)
+        dD_p = torch.empty((B, 4 * D), **f32)
+        with torch.cuda.device(dev):
+            with timed_launch("outnorm_gate_bwd", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_outnorm_gate_bwd(ptr(dout), ptr(merged), ptr(zv), ptr(g32), ptr(b32), ptr(dy), ptr(dz),
+                                                ptr(gb_part), i64(B * H * W), _c_int(D), i64(z_px), ctypes.c_float(eps),
+                                                _c_int(dtype_code(zv)), stream_ptr(dev))
+            check(st, "mmb_outnorm_gate_bwd")
+            with timed_launch("ss2d_core_bwd", f"B={B},L={H * W},D={D},R={R}"):
+                st = lib().mmb_ss2d_core_bwd(ptr(xc), ptr(proj), ptr(dy), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds),
+                                             ptr(hsave), ptr(dudir), ptr(ddraw), ptr(dBC), ptr(dA_p), ptr(dD_p),
+                                             _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(N), _c_int(R), _c_int(rp),
+                                             _c_int(dtype_code(xc)), stream_ptr(dev))
+            check(st, "mmb_ss2d_core_bwd")
+        gb = gb_part.sum(0)
+        dxc = dudir.sum(3).to(xc.dtype)
+        flat = ddraw.view(B * H * W, 4, D)
+        dt_in = proj.view(B * H * W, 4, 32 + rp)[:, :, 32:32 + R]
+        ddt = torch.einsum("tkd,kdr->tkr", flat, Wdt)                       # (T, 4, R)
+        dWdt = torch.einsum("tkd,tkr->kdr", flat, dt_in)
+        dbias = flat.sum(0)
+        dproj = torch.zeros((B, H, W, 4, 32 + rp), **f32)
+        dproj[..., :32] = dBC[0] if tiles == 1 else dBC.sum(0)
+        dproj[..., 32:32 + R] = ddt.view(B, H, W, 4, R)
+        return (dxc, dproj, dz, dWdt.to(wdt_t), dbias.to(b_t), dA_p.sum(0).to(a_t), dD_p.sum(0).to(d_t),
+                gb[0].to(gamma.dtype), gb[1].to(beta.dtype), None, None, None)
+
+
+def ss2d_inner_train(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
+                     eps, d_state, dt_rank):
+    """Differentiable twin of ops.ss2d_inner (same kernels forward, hand-written kernels backward)."""
+    B, H, W, D2 = xz.shape
+    D = D2 // 2
+    x, z = xz[..., :D], xz[..., D:]
+    w_packed = ops.pack_x_proj(x_proj_weight.float(), d_state, dt_rank)
+    if xz.dtype == torch.bfloat16 and D % 8 == 0:
+        xc = DwConvSiluFn.apply(x, conv_w, conv_b, torch.bfloat16)
+        proj = _MmF32Out.apply(xc.view(-1, D), w_packed).view(B, H, W, 4, -1)
+    else:
+        xc = DwConvSiluFn.apply(x, conv_w, conv_b, torch.float32)
+        proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+    A = -torch.exp(A_logs.float())
+    return CoreNormGateFn.apply(xc, proj, z, dt_projs_weight, dt_projs_bias, A, Ds.float(), norm_w, norm_b, eps,
+                                d_state, dt_rank)
+
+
+class ShuffleCatResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, left, ssm, inp):
+        ctx.meta = (left.dtype, ssm.dtype, inp.dtype, ssm.shape)
+        return ops.shuffle_cat_residual_raw(left, ssm, inp)
+
+    @staticmethod
+    def backward(ctx, g):
+        ldt, sdt, idt, (B, H, W, c) = ctx.meta
+        dev = g.device
+        g = g.contiguous()
+        bdt = sdt if sdt in (torch.float32, torch.bfloat16) and (sdt == g.dtype or g.dtype == torch.float32) else g.dtype
+        dleft = torch.empty((B, H, W, c), dtype=bdt, device=dev)
+        dssm = torch.empty((B, H, W, c), dtype=bdt, device=dev)
+        with torch.cuda.device(dev), timed_launch("shuffle_cat_residual_bwd", f"B={B},L={H * W},c={c}"):
+            st = lib().mmb_shuffle_cat_residual_bwd(ptr(g), ptr(dleft), ptr(dssm), i64(B * H * W), _c_int(c),
+                                                    _c_int(dtype_code(g)), _c_int(dtype_code(dleft)), stream_ptr(dev))
+        check(st, "mmb_shuffle_cat_residual_bwd")
+        return dleft.to(ldt), dssm.to(sdt), g.to(idt)

@@ -178,16 +178,17 @@ class SS2D(nn.Module):
         xz = self.in_proj(x)                                                          # (B, H, W, 2D)
         if xz.dtype == torch.float16:
             xz = xz.float()
-        y = ops.ss2d_inner(xz, self.conv2d.weight, self.conv2d.bias, self.x_proj_weight, self.dt_projs_weight,
+        inner = ops.ss2d_inner
+        if ops.needs_autograd(xz, self.conv2d.weight, self.x_proj_weight, self.dt_projs_weight, self.A_logs, self.Ds,
+                              self.out_norm.weight):
+            from .fused_autograd import ss2d_inner_train as inner      # same kernels + their backward kernels
+        y = inner(xz, self.conv2d.weight, self.conv2d.bias, self.x_proj_weight, self.dt_projs_weight,
                            self.dt_projs_bias, self.A_logs, self.Ds, self.out_norm.weight, self.out_norm.bias,
                            self.out_norm.eps, self.d_state, self.dt_rank)
         return self.out_proj(y.to(xz.dtype) if y.dtype != xz.dtype else y)
 
     def forward(self, x: torch.Tensor, **kwargs):
-        # training (autograd) goes through the reference op order with selective_scan_fn's own backward
-        # kernel; the fused inference kernels have no backward in this round
-        training_graph = ops.needs_autograd(x, self.in_proj.weight, self.x_proj_weight, self.A_logs)
-        use_fused = (self.fused and x.is_cuda and self.d_conv == 3 and not training_graph and ops.fused_available())
+        use_fused = self.fused and x.is_cuda and self.d_conv == 3 and ops.fused_available()
         out = self._forward_fused(x) if use_fused else self._forward_reference_order(x)
         return out if self.dropout is None else self.dropout(out)
 

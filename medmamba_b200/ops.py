@@ -52,59 +52,74 @@ def dwconv3x3_silu(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=torch.
     """x: (B, H, W, D) channels-last view (channel stride 1, uniform pixel pitch) -> dense (B, H, W, D)."""
     dev = require_cuda(x, weight, bias)
     B, H, W, D = x.shape
-    if x.stride(3) != 1 or x.stride(1) != W * x.stride(2):
-        x = x.contiguous()
+    x, x_px, x_bs = _token_view(x, uniform_batch=False)
     out = torch.empty((B, H, W, D), dtype=out_dtype, device=dev)
     w = weight.detach().float().contiguous()
     bs = bias.detach().float().contiguous() if bias is not None else None
     with torch.cuda.device(dev), timed_launch("dwconv3x3_silu_fwd", f"B={B},L={H * W},D={D}"):
         st = lib().mmb_dwconv3x3_silu_fwd(ptr(x), ptr(w), ptr(bs), ptr(out), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
-                                          i64(x.stride(2)), i64(x.stride(0)), _c_int(dtype_code(x)),
+                                          i64(x_px), i64(x_bs), _c_int(dtype_code(x)),
                                           _c_int(dtype_code(out)), stream_ptr(dev))
     check(st, "mmb_dwconv3x3_silu_fwd")
     return out
 
 
-def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int) -> torch.Tensor:
+def core_train_blocks(H: int, W: int) -> int:
+    n = lib().mmb_ss2d_core_train_blocks(_c_int(H), _c_int(W))
+    if n < 0:
+        raise ValueError(f"unsupported token grid {H}x{W}")
+    return n
+
+
+def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int, save_states: bool = False):
     """xc (B, H, W, D) fp32 or bf16, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) fp32."""
     dev = require_cuda(xc, proj, Wdt, dt_bias, A, Ds)
     B, H, W, D = xc.shape
     rp = dt_pad(dt_rank)
     assert proj.shape == (B, H, W, 4, 32 + rp) and proj.is_contiguous() and xc.is_contiguous()
     ydir = torch.empty((B, H, W, 4, D), dtype=torch.float32, device=dev)
+    hsave = (torch.empty((B, 4, core_train_blocks(H, W), D, 16), dtype=torch.float32, device=dev)
+             if save_states else None)
     with torch.cuda.device(dev), timed_launch("ss2d_core_fwd", f"B={B},L={H * W},D={D},R={dt_rank}"):
-        st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir),
+        st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir), ptr(hsave),
                                      _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
                                      _c_int(rp), _c_int(dtype_code(xc)), stream_ptr(dev))
     check(st, "mmb_ss2d_core_fwd")
-    return ydir
+    return (ydir, hsave) if save_states else ydir
 
 
 def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
     """ydir (B, H, W, 4, D) fp32, z (B, H, W, D) view -> LayerNorm(sum of directions) * SiLU(z)."""
     dev = require_cuda(ydir, z, gamma, beta)
     B, H, W, K, D = ydir.shape
-    if z.stride(3) != 1 or z.stride(1) != W * z.stride(2) or z.stride(0) != H * W * z.stride(2):
-        z = z.contiguous()
+    z, z_px, _ = _token_view(z)
     out = torch.empty((B, H, W, D), dtype=z.dtype, device=dev)
     merged = torch.empty((B, H, W, D), dtype=torch.float32, device=dev) if want_merged else None
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
     with torch.cuda.device(dev), timed_launch("outnorm_gate_fwd", f"B={B},L={H * W},D={D}"):
         st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged), i64(B * H * W),
-                                        _c_int(D), i64(z.stride(2)), ctypes.c_float(eps), _c_int(dtype_code(z)),
+                                        _c_int(D), i64(z_px), ctypes.c_float(eps), _c_int(dtype_code(z)),
                                         _c_int(dtype_code(out)), stream_ptr(dev))
     check(st, "mmb_outnorm_gate_fwd")
     return (out, merged) if want_merged else out
 
 
-def _token_view(t: torch.Tensor):
-    """(B, H, W, C) with channel stride 1 and a uniform pixel pitch, else a dense copy."""
+def _token_view(t: torch.Tensor, uniform_batch: bool = True):
+    """(B, H, W, C) as a token matrix: returns (tensor, pixel_stride, batch_stride) with channel stride 1
+    and rows h, w at a uniform pixel pitch (a dense copy is made otherwise).  Strides of size-1
+    dimensions are ignored, as torch does."""
     B, H, W, C = t.shape
-    px = t.stride(2)
-    if t.stride(3) != 1 or t.stride(1) != W * px or t.stride(0) != H * W * px:
+    if t.is_contiguous():
+        return t, C, H * W * C
+    px = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else C)
+    bs = t.stride(0) if B > 1 else H * W * px
+    ok = ((C == 1 or t.stride(3) == 1) and (W == 1 or t.stride(2) == px) and (H == 1 or t.stride(1) == W * px)
+          and px >= C and (not uniform_batch or bs == H * W * px))
+    if not ok:
         t = t.contiguous()
-    return t, t.stride(2)
+        return t, C, H * W * C
+    return t, px, bs
 
 
 def shuffle_cat_residual_raw(left, ssm, inp) -> torch.Tensor:
@@ -114,9 +129,9 @@ def shuffle_cat_residual_raw(left, ssm, inp) -> torch.Tensor:
     bdt = ssm.dtype
     if not (bdt == dt or (dt == torch.float32 and bdt in (torch.bfloat16, torch.float16))):
         bdt = dt
-    left, lp = _token_view(left.to(bdt))
-    ssm, sp = _token_view(ssm.to(bdt))
-    inp, ip = _token_view(inp)
+    left, lp, _ = _token_view(left.to(bdt))
+    ssm, sp, _ = _token_view(ssm.to(bdt))
+    inp, ip, _ = _token_view(inp)
     out = torch.empty((B, H, W, 2 * c), dtype=dt, device=dev)
     with torch.cuda.device(dev), timed_launch("shuffle_cat_residual_fwd", f"B={B},L={H * W},c={c}"):
         st = lib().mmb_shuffle_cat_residual_fwd(ptr(left), ptr(ssm), ptr(inp), ptr(out), i64(B * H * W), _c_int(c),
@@ -159,23 +174,10 @@ def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias
     return outnorm_gate(ydir, z, norm_w, norm_b, eps)
 
 
-class _ShuffleCatResidual(torch.autograd.Function):
-    """The backward of an interleave + add is a de-interleave: plain strided views, no kernel needed."""
-
-    @staticmethod
-    def forward(ctx, left, ssm, inp):
-        ctx.dtypes = (left.dtype, ssm.dtype, inp.dtype)
-        return shuffle_cat_residual_raw(left, ssm, inp)
-
-    @staticmethod
-    def backward(ctx, g):
-        dl, ds, di = ctx.dtypes
-        return g[..., 0::2].to(dl), g[..., 1::2].to(ds), g.to(di)
-
-
 def shuffle_cat_residual(left, ssm, inp):
     if torch.is_grad_enabled() and any(t.requires_grad for t in (left, ssm, inp)):
-        return _ShuffleCatResidual.apply(left, ssm, inp)
+        from .fused_autograd import ShuffleCatResidualFn
+        return ShuffleCatResidualFn.apply(left, ssm, inp)
     return shuffle_cat_residual_raw(left, ssm, inp)
 
 

@@ -9,6 +9,7 @@ ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--unfused", action="store_true")
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--bf16", action="store_true")
 args = ap.parse_args()
 torch.manual_seed(0)
 net = mm.medmamba_t(6).cuda().eval()
@@ -17,7 +18,8 @@ if args.unfused:
         if isinstance(m, mm.SS2D):
             m.fused = False
 x = torch.randn(args.batch, 3, 224, 224, device="cuda")
-with torch.no_grad():
+amp = torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.bf16)
+with torch.no_grad(), amp:
     for _ in range(2):
         net(x)
     torch.cuda.synchronize()
