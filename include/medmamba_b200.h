@@ -160,14 +160,15 @@ int mmb_ss2d_core_bwd_tiles(int D);
 
 /* Gradient of mmb_ss2d_core_fwd given dY (batch, H, W, D) fp32 -- the gradient of the merged sum, identical for
  * the four direction slices of ydir.  xc, proj, Wdt, dt_bias, A, Ds as in the forward; hsave as written by it.
- *   dudir    : (batch, H, W, 4, D) fp32 -- d xc through direction k's `u` (sum over k = that part of d xc)
- *   ddraw    : (batch, H, W, 4, D) fp32 -- d (Wdt . dt_r + dt_bias); the host derives d dt_r, dWdt, d dt_bias
- *   dBC_part : (tiles, batch, H, W, 4, 32) fp32 -- [0,16) dB_n, [16,32) dC_n; sum over axis 0
- *   dA_part  : (batch, 4*D, dstate) fp32;  dD_part: (batch, 4*D) fp32 -- sum over axis 0 */
+ *   dudir      : (batch, H, W, 4, D) fp32 -- d xc through direction k's `u` (sum over k = that part of d xc)
+ *   dproj_part : (tiles, batch, H, W, 4, 32 + dt_pad) fp32 -- gradient of proj in proj's own layout
+ *                [dB_n | dC_n | d dt_r]; sum over axis 0
+ *   dA_part    : (batch, 4*D, dstate);  dW_part: (batch, 4*D, dt_pad) (= dWdt, first dt_rank columns);
+ *   dD_part, db_part : (batch, 4*D) (= dDs, d dt_bias) -- all fp32, sum over axis 0 */
 int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const float* Wdt,
                       const float* dt_bias, const float* A, const float* Ds, const float* hsave,
-                      float* dudir, float* ddraw, float* dBC_part, float* dA_part, float* dD_part,
-                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
+                      float* dudir, float* dproj_part, float* dA_part, float* dW_part, float* dD_part,
+                      float* db_part, int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
                       void* stream);
 
 /* Backward of mmb_outnorm_gate_fwd: dout (tokens, D) dense in z_dtype, ymerged from the forward ->

@@ -1,6 +1,5 @@
-// Fused SS2D core, backward.  Gradient of mmb_ss2d_core_fwd w.r.t. xc (per direction), the raw delta
-// (= Wdt.dt_r + bias, from which the host derives d dt_r, dWdt and d dt_bias with two small GEMMs),
-// B_n, C_n, A and D.  Formulas: SURVEY.md Appendix B; the cross-scan / cross-merge index maps are
+// Fused SS2D core, backward.  Gradient of mmb_ss2d_core_fwd w.r.t. xc (per direction), proj (dB_n, dC_n,
+// d dt_r), Wdt, dt_bias, A and D.  Formulas: SURVEY.md Appendix B; the cross-scan / cross-merge index maps are
 // the forward's (Appendix A) -- the backward of a gather by index is a scatter to the same index,
 // so "cross-merge of the per-direction du" is again just the store address.
 //
@@ -26,28 +25,30 @@ constexpr int kBwdStages = 3;
 
 struct CoreBwdParams {
     const float* Wdt; const float* bias; const float* A; const float* Ds; const float* hsave;
-    float* dudir; float* ddraw;     // (B, L, 4, D)
-    float* dBC;                     // (tiles, B, L, 4, 32)
+    float* dudir;                   // (B, L, 4, D)
+    float* dproj;                   // (tiles, B, L, 4, CP): [dB_n | dC_n | d dt_r]
     float* dA_part;                 // (B, 4D, N)
-    float* dD_part;                 // (B, 4D)
+    float* dW_part;                 // (B, 4D, RP)
+    float* dD_part; float* db_part; // (B, 4D)
     int B, H, W, L, D, N, R, CT, tiles, NBmax;
     int T_row, NB_row, nw, T_col, NI_col, NO_col, cap;
 };
 
 template <int RP, typename xc_t>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(192, 2)
 ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmd_row, const __grid_constant__ CUtensorMap tmd_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
                      const CoreBwdParams p) {
     constexpr int S = 4, NS = 4, CP = 32 + RP, TB = kTrainCap, XE = (int)sizeof(xc_t);
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int RW = CP;                      // floats per step in the cross-channel reduction tiles
     const int xpad = (p.cap * p.CT * XE + 127) & ~127, dpad = (p.cap * p.CT * 4 + 127) & ~127,
-              ppad = (p.cap * CP * 4 + 127) & ~127;
-    const int stage_bytes = xpad + dpad + ppad;
+              ppad = (p.cap * CP * 4 + 127) & ~127, hpad = p.CT * kMaxState * 4;
+    const int stage_bytes = xpad + dpad + ppad + hpad;
     const int nwarps = blockDim.x >> 5;
-    float* swred = reinterpret_cast<float*>(smem_raw + kBwdStages * stage_bytes);     // [2][nwarps][TB][32]
-    int* spos = reinterpret_cast<int*>(swred + 2 * nwarps * TB * 32);                 // [2][TB]
+    float* swred = reinterpret_cast<float*>(smem_raw + kBwdStages * stage_bytes);     // [2][nwarps][TB][RW]
+    int* spos = reinterpret_cast<int*>(swred + 2 * nwarps * TB * RW);                 // [2][TB]
     uint64_t* full = reinterpret_cast<uint64_t*>(spos + 2 * TB);
     uint64_t* empty = full + kBwdStages;
 
@@ -64,18 +65,23 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         uint8_t* xs = smem_raw + s * stage_bytes;
         uint8_t* ds = xs + xpad;
         uint8_t* ps = ds + dpad;
+        uint8_t* hs = ps + ppad;
+        // checkpoint after block jb-1 = state at the start of block jb: CT x 16 floats, contiguous
+        const int hbytes = jb > 0 ? min(p.CT, p.D - c0) * kMaxState * 4 : 0;
         if (!colview) {
-            mbar_expect_tx(&full[s], p.T_row * (p.CT * (XE + 4) + CP * 4));
+            mbar_expect_tx(&full[s], p.T_row * (p.CT * (XE + 4) + CP * 4) + hbytes);
             tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
             tma_load_3d(ds, &tmd_row, &full[s], c0, blk * p.T_row, b);
             tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
         } else {
             const int o = blk / p.NI_col, i = blk % p.NI_col;
-            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * (XE + 4) + CP * 4));
+            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * (XE + 4) + CP * 4) + hbytes);
             tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
             tma_load_4d(ds, &tmd_col, &full[s], c0, o * p.nw, i * p.T_col, b);
             tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
         }
+        if (hbytes)
+            bulk_load_1d(hs, p.hsave + ((((int64_t)b * 4 + k) * p.NBmax + (jb - 1)) * p.D + c0) * kMaxState, hbytes, &full[s]);
     };
 
     if (tid == 0) {
@@ -91,7 +97,7 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     const int row = k * p.D + (cvalid ? c : 0);
     const int lane_base = lane & ~(S - 1);
 
-    float Ap[NS], Araw[NS], gcar[NS], dA[NS], Wd[RP];
+    float Ap[NS], Araw[NS], gcar[NS], dA[NS], Wd[RP], Wq[RP / 4], dWq[RP / 4];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         const int n = 4 * q + j;
@@ -101,12 +107,17 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     }
 #pragma unroll
     for (int r = 0; r < RP; ++r) Wd[r] = (cvalid && r < p.R) ? p.Wdt[(int64_t)row * p.R + r] : 0.f;
+    // lane q owns the dt ranks r = q, q+4, ... of its channel for dWdt and d dt_r
+#pragma unroll
+    for (int i = 0; i < RP / 4; ++i) {
+        Wq[i] = q == 0 ? Wd[4 * i] : q == 1 ? Wd[4 * i + 1] : q == 2 ? Wd[4 * i + 2] : Wd[4 * i + 3];
+        dWq[i] = 0.f;
+    }
     const float bias = cvalid ? p.bias[row] : 0.f;
     const float Dd = cvalid ? p.Ds[row] : 0.f;
-    float dD_acc = 0.f;
+    float dD_acc = 0.f, db_acc = 0.f;
     const int64_t gstride = 4 * (int64_t)p.D;
     float* dub = p.dudir + ((int64_t)b * p.L * 4 + k) * p.D + c;
-    float* ddb = p.ddraw + ((int64_t)b * p.L * 4 + k) * p.D + c;
 
     for (int it = 0; it < NB; ++it) {
         const int s = it % kBwdStages, ph = (it / kBwdStages) & 1;
@@ -134,24 +145,24 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             slot_l = hh * nwbox + ww;
             pos_l = pbase + hh * psh + ww;
         }
-        // state at the start of the block: the forward's checkpoint after block jb-1
-        float h[NS];
-        if (jb > 0 && cvalid) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(
-                p.hsave + ((((int64_t)b * 4 + k) * p.NBmax + (jb - 1)) * p.D + c) * kMaxState + 4 * q));
-            h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
-        } else {
-            h[0] = h[1] = h[2] = h[3] = 0.f;
-        }
         const xc_t* xs = reinterpret_cast<const xc_t*>(smem_raw + s * stage_bytes) + cl;
         const float* dys = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad) + cl;
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad + dpad);
-        float* wred = swred + (it & 1) * nwarps * TB * 32 + warp * TB * 32;
+        const float* hs = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad + dpad + ppad);
+        float* wred = swred + (it & 1) * nwarps * TB * RW + warp * TB * RW;
         if (warp == 0 && lane < TB) {
             const int ti = lane < nsteps ? (rev ? nsteps - 1 - lane : lane) : 0;
             spos[(it & 1) * TB + lane] = __shfl_sync(0xffu, pos_l, ti);
         }
         mbar_wait(&full[s], ph);
+        // state at the start of the block: the forward's checkpoint after block jb-1 (staged with the tiles)
+        float h[NS];
+        if (jb > 0 && cvalid) {
+            const float4 v = *reinterpret_cast<const float4*>(hs + cl * kMaxState + 4 * q);
+            h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
+        } else {
+            h[0] = h[1] = h[2] = h[3] = 0.f;
+        }
 
         // ---- phase A: forward through the block (time order), history in registers ---------------------
         int slot[TB];
@@ -223,10 +234,22 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             adu += __shfl_xor_sync(0xffffffffu, adu, 1); adu += __shfl_xor_sync(0xffffffffu, adu, 2);
             adl += __shfl_xor_sync(0xffffffffu, adl, 1); adl += __shfl_xor_sync(0xffffffffu, adl, 2);
             const int pos = __shfl_sync(0xffffffffu, pos_l, ok ? (rev ? nsteps - 1 - tl : tl) : 0);
+            const float ddr = adl * sg[tl];                  // d(Wdt.dt_r + bias); sg = 0 on masked steps
             if (ok && cvalid && q == 0) {
                 dub[pos * gstride] = fmaf(Dd, dy, dl[tl] * adu);
-                ddb[pos * gstride] = adl * sg[tl];
                 dD_acc = fmaf(dy, uu, dD_acc);
+            }
+            db_acc += ddr;
+            // dWdt[c][r] += ddr * dt_r and d dt_r += Wdt[c][r] * ddr (summed over the warp's 8 channels)
+#pragma unroll
+            for (int i = 0; i < RP / 4; ++i) {
+                const float dtv = ps[slot[tl] * CP + 32 + q + 4 * i];
+                dWq[i] = fmaf(ddr, dtv, dWq[i]);
+                float w = Wq[i] * ddr;
+                w += __shfl_xor_sync(0xffffffffu, w, 4);
+                w += __shfl_xor_sync(0xffffffffu, w, 8);
+                w += __shfl_xor_sync(0xffffffffu, w, 16);
+                if (lane < 4) wred[tl * RW + 32 + q + 4 * i] = w;
             }
             // sum v[0..7] over the 8 channels of this warp (lanes with equal q)
 #pragma unroll
@@ -242,7 +265,7 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             {
                 const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
                 const int n = 4 * q + (idx & 3);
-                wred[tl * 32 + (idx < 4 ? n : 16 + n)] = v[0];
+                wred[tl * RW + (idx < 4 ? n : 16 + n)] = v[0];
             }
         }
         __syncwarp();
@@ -250,13 +273,13 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         __syncthreads();
         // ---- this channel tile's partial dB / dC of the block, warps added in fixed order ---------------
         {
-            const float* wr = swred + (it & 1) * nwarps * TB * 32;
-            float* out = p.dBC + (((int64_t)tile * p.B + b) * p.L * 4 + k) * 32;
-            for (int idx = tid; idx < nsteps * 32; idx += blockDim.x) {
-                const int tl = idx >> 5, vv = idx & 31;
+            const float* wr = swred + (it & 1) * nwarps * TB * RW;
+            float* out = p.dproj + (((int64_t)tile * p.B + b) * p.L * 4 + k) * RW;
+            for (int idx = tid; idx < nsteps * RW; idx += blockDim.x) {
+                const int tl = idx / RW, vv = idx - tl * RW;
                 float sum = 0.f;
-                for (int w = 0; w < nwarps; ++w) sum += wr[(w * TB + tl) * 32 + vv];
-                out[(int64_t)spos[(it & 1) * TB + tl] * 4 * 32 + vv] = sum;
+                for (int w = 0; w < nwarps; ++w) sum += wr[(w * TB + tl) * RW + vv];
+                out[(int64_t)spos[(it & 1) * TB + tl] * 4 * RW + vv] = sum;
             }
         }
     }
@@ -266,8 +289,12 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             const int n = 4 * q + j;
             if (n < p.N) p.dA_part[((int64_t)b * 4 * p.D + row) * p.N + n] = dA[j];
         }
-        float dd = dD_acc;     // only q == 0 accumulated
-        if (q == 0) p.dD_part[(int64_t)b * 4 * p.D + row] = dd;
+#pragma unroll
+        for (int i = 0; i < RP / 4; ++i) p.dW_part[((int64_t)b * 4 * p.D + row) * RP + q + 4 * i] = dWq[i];
+        if (q == 0) {
+            p.dD_part[(int64_t)b * 4 * p.D + row] = dD_acc;
+            p.db_part[(int64_t)b * 4 * p.D + row] = db_acc;
+        }
     }
 }
 
@@ -304,8 +331,8 @@ static int launch_core_bwd(CoreBwdParams& p, const void* xc, const float* dY, co
     }
     const int threads = p.CT * 4, nwarps = threads / 32;
     const size_t xpad = ((size_t)p.cap * p.CT * XE + 127) & ~(size_t)127, dpad = ((size_t)p.cap * p.CT * 4 + 127) & ~(size_t)127,
-                 ppad = ((size_t)p.cap * CP * 4 + 127) & ~(size_t)127;
-    const size_t smem = kBwdStages * (xpad + dpad + ppad) + (size_t)2 * nwarps * kTrainCap * 32 * 4 + 2 * kTrainCap * 4 +
+                 ppad = ((size_t)p.cap * CP * 4 + 127) & ~(size_t)127, hpad = (size_t)p.CT * kMaxState * 4;
+    const size_t smem = kBwdStages * (xpad + dpad + ppad + hpad) + (size_t)2 * nwarps * kTrainCap * CP * 4 + 2 * kTrainCap * 4 +
                         2 * kBwdStages * sizeof(uint64_t);
     auto kern = ss2d_core_bwd_kernel<RP, xc_t>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -329,8 +356,8 @@ static int dispatch_core_bwd(int dt_pad, CoreBwdParams& p, const void* xc, const
     }
 }
 
-static int core_bwd_ct(int D) {            // channels per CTA: <= 96 (384 threads), a multiple of 8
-    const int tiles = (D + 95) / 96;
+static int core_bwd_ct(int D) {            // channels per CTA: <= 48 (192 threads, two CTAs per SM), a multiple of 8
+    const int tiles = (D + 47) / 48;
     int ct = (D + tiles - 1) / tiles;
     return (ct + 7) / 8 * 8;
 }
@@ -345,12 +372,12 @@ extern "C" int mmb_ss2d_core_bwd_tiles(int D) {
 
 extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const float* Wdt,
                                  const float* dt_bias, const float* A, const float* Ds, const float* hsave,
-                                 float* dudir, float* ddraw, float* dBC_part, float* dA_part, float* dD_part,
-                                 int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
+                                 float* dudir, float* dproj_part, float* dA_part, float* dW_part, float* dD_part,
+                                 float* db_part, int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
                                  void* stream) {
     using namespace mmb;
-    if (!xc || !proj || !dY || !Wdt || !dt_bias || !A || !Ds || !hsave || !dudir || !ddraw || !dBC_part || !dA_part ||
-        !dD_part) return MMB_ERR_INVALID_ARG;
+    if (!xc || !proj || !dY || !Wdt || !dt_bias || !A || !Ds || !hsave || !dudir || !dproj_part || !dA_part || !dW_part ||
+        !dD_part || !db_part) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0 || dstate <= 0 || dt_rank <= 0) return MMB_ERR_INVALID_ARG;
     if (dstate > kMaxState || dt_pad != mmb_ss2d_core_dt_pad(dt_rank)) return MMB_ERR_UNSUPPORTED;
     if (xc_dtype != MMB_F32 && xc_dtype != MMB_BF16) return MMB_ERR_UNSUPPORTED;
@@ -362,7 +389,7 @@ extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float*
     if (!core_geometry(H, W, kTrainCap, g)) return MMB_ERR_UNSUPPORTED;
     CoreBwdParams p;
     p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds; p.hsave = hsave;
-    p.dudir = dudir; p.ddraw = ddraw; p.dBC = dBC_part; p.dA_part = dA_part; p.dD_part = dD_part;
+    p.dudir = dudir; p.dproj = dproj_part; p.dA_part = dA_part; p.dW_part = dW_part; p.dD_part = dD_part; p.db_part = db_part;
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank;
     p.CT = core_bwd_ct(D); p.tiles = (D + p.CT - 1) / p.CT; p.NBmax = g.nblocks_max();
     p.T_row = g.T_row; p.NB_row = g.NB_row; p.nw = g.nw; p.T_col = g.T_col; p.NI_col = g.NI_col; p.NO_col = g.NO_col;

@@ -103,10 +103,11 @@ class CoreNormGateFn(torch.autograd.Function):
         gb_part = torch.empty((_partial_blocks(), 2, D), **f32)
         tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(D))
         dudir = torch.empty((B, H, W, 4, D), **f32)
-        ddraw = torch.empty((B, H, W, 4, D), **f32)
-        dBC = torch.empty((tiles, B, H, W, 4, 32), **f32)
+        dproj_p = torch.empty((tiles, B, H, W, 4, 32 + rp), **f32)
         dA_p = torch.empty((B, 4 * D, N), **f32)
+        dW_p = torch.empty((B, 4 * D, rp), **f32)
         dD_p = torch.empty((B, 4 * D), **f32)
+        db_p = torch.empty((B, 4 * D), **f32)
         with torch.cuda.device(dev):
             with timed_launch("outnorm_gate_bwd", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_outnorm_gate_bwd(ptr(dout), ptr(merged), ptr(zv), ptr(g32), ptr(b32), ptr(dy), ptr(dz),
@@ -115,22 +116,16 @@ class CoreNormGateFn(torch.autograd.Function):
             check(st, "mmb_outnorm_gate_bwd")
             with timed_launch("ss2d_core_bwd", f"B={B},L={H * W},D={D},R={R}"):
                 st = lib().mmb_ss2d_core_bwd(ptr(xc), ptr(proj), ptr(dy), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds),
-                                             ptr(hsave), ptr(dudir), ptr(ddraw), ptr(dBC), ptr(dA_p), ptr(dD_p),
-                                             _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(N), _c_int(R), _c_int(rp),
+                                             ptr(hsave), ptr(dudir), ptr(dproj_p), ptr(dA_p), ptr(dW_p), ptr(dD_p),
+                                             ptr(db_p), _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(N), _c_int(R), _c_int(rp),
                                              _c_int(dtype_code(xc)), stream_ptr(dev))
             check(st, "mmb_ss2d_core_bwd")
         gb = gb_part.sum(0)
         dxc = dudir.sum(3).to(xc.dtype)
-        flat = ddraw.view(B * H * W, 4, D)
-        dt_in = proj.view(B * H * W, 4, 32 + rp)[:, :, 32:32 + R]
-        ddt = torch.einsum("tkd,kdr->tkr", flat, Wdt)                       # (T, 4, R)
-        dWdt = torch.einsum("tkd,tkr->kdr", flat, dt_in)
-        dbias = flat.sum(0)
-        dproj = torch.zeros((B, H, W, 4, 32 + rp), **f32)
-        dproj[..., :32] = dBC[0] if tiles == 1 else dBC.sum(0)
-        dproj[..., 32:32 + R] = ddt.view(B, H, W, 4, R)
-        return (dxc, dproj, dz, dWdt.to(wdt_t), dbias.to(b_t), dA_p.sum(0).to(a_t), dD_p.sum(0).to(d_t),
-                gb[0].to(gamma.dtype), gb[1].to(beta.dtype), None, None, None)
+        dproj = dproj_p[0] if tiles == 1 else dproj_p.sum(0)
+        dWdt = dW_p.sum(0)[:, :R].reshape(4, D, R)
+        return (dxc, dproj, dz, dWdt.to(wdt_t), db_p.sum(0).view(4, D).to(b_t), dA_p.sum(0).to(a_t),
+                dD_p.sum(0).to(d_t), gb[0].to(gamma.dtype), gb[1].to(beta.dtype), None, None, None)
 
 
 def ss2d_inner_train(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
