@@ -148,6 +148,15 @@ int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* 
                                  int64_t ssm_pixel_stride, int64_t inp_pixel_stride, int branch_dtype,
                                  int res_dtype, void* stream);
 
+/* ---- callers either side of the path ---- */
+
+/* LayerNorm over the channels of a channels-last token matrix: ln_1 on the strided right half of the residual
+ * stream (MedMamba.py:351), the patch-embed norm (:75), the patch-merging norm (:116).  Inference path.
+ *   x : (tokens, D) view, channel stride 1, pixel stride x_pixel_stride;  out: (tokens, D) dense
+ * D % 4 == 0, D <= 2048. */
+int mmb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* out, int64_t tokens, int D,
+                      int64_t x_pixel_stride, float eps, int in_dtype, int out_dtype, void* stream);
+
 /* ---- backward of the fused path (training; loss.backward(), train.py:284).  Parameter gradients come back
  * as per-CTA / per-batch partials that the caller sums over the leading axis: no float atomics, results are
  * bit-reproducible. ---- */

@@ -133,6 +133,56 @@ outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Plain LayerNorm over the channels of a channels-last token matrix (warp per token).  Used for ln_1 on the
+// strided right half of the residual stream (MedMamba.py:351), the patch-embed norm (:75) and the patch-merging
+// norm (:116): rows of 48..1536 channels, for which a block-per-row LayerNorm leaves most threads idle.
+template <int V, typename in_t, typename out_t>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     out_t* __restrict__ out, int64_t tokens, int D, int64_t x_pix, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int C4 = D / 4;
+    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+        float4 v[V];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            v[i] = c4 < C4 ? load4<in_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (lane + 32 * i < C4) {
+                v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        const float rstd = rsqrtf(sq / (float)D + eps);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+                float4 o;
+                o.x = fmaf(v[i].x * rstd, g.x, bt.x); o.y = fmaf(v[i].y * rstd, g.y, bt.y);
+                o.z = fmaf(v[i].z * rstd, g.z, bt.z); o.w = fmaf(v[i].w * rstd, g.w, bt.w);
+                store4<out_t>(out + tok * D + 4 * c4, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
 // (torch.cat + channel_shuffle(groups=2) + residual).  A thread produces 8 output channels.
 template <typename TB, typename T>   // TB: branch dtype (left, ssm); T: residual stream dtype (inp, out)
@@ -255,6 +305,40 @@ extern "C" int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const floa
     if (z_dtype == MMB_F16) MMB_ON_V(__half);
 #undef MMB_ON_V
 #undef MMB_ON
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* out, int64_t tokens, int D,
+                                 int64_t x_pixel_stride, float eps, int in_dtype, int out_dtype, void* stream) {
+    using namespace mmb;
+    if (!x || !gamma || !beta || !out) return MMB_ERR_INVALID_ARG;
+    if (tokens < 0 || D <= 0) return MMB_ERR_INVALID_ARG;
+    if (D % 4 != 0 || D > 2048 || x_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    if (tokens == 0) return MMB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(tokens * 32, 256);
+#define MMB_LN(V, TI, TO)                                                                                        \
+    do {                                                                                                         \
+        if (!aligned_for4<TI>(x) || !aligned_for4<TO>(out)) return MMB_ERR_UNSUPPORTED;                          \
+        layernorm_fwd_kernel<V, TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta,       \
+            reinterpret_cast<TO*>(out), tokens, D, x_pixel_stride, eps);                                         \
+        return launch_status();                                                                                  \
+    } while (0)
+#define MMB_LN_V(TI, TO)                                                                                         \
+    do {                                                                                                         \
+        if (D <= 128) MMB_LN(1, TI, TO);                                                                         \
+        if (D <= 256) MMB_LN(2, TI, TO);                                                                         \
+        if (D <= 512) MMB_LN(4, TI, TO);                                                                         \
+        if (D <= 1024) MMB_LN(8, TI, TO);                                                                        \
+        MMB_LN(16, TI, TO);                                                                                      \
+    } while (0)
+    if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_LN_V(float, float);
+    if (in_dtype == MMB_F32 && out_dtype == MMB_BF16) MMB_LN_V(float, __nv_bfloat16);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16) MMB_LN_V(__nv_bfloat16, __nv_bfloat16);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_LN_V(__nv_bfloat16, float);
+#undef MMB_LN_V
+#undef MMB_LN
     return MMB_ERR_UNSUPPORTED;
 }
 

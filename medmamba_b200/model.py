@@ -38,7 +38,11 @@ class PatchEmbed2D(nn.Module):
 
     def forward(self, x):
         x = self.proj(x).permute(0, 2, 3, 1)
-        return x if self.norm is None else self.norm(x)
+        if self.norm is None:
+            return x
+        if ops.fast_layernorm_ok(x, self.norm):
+            return ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype=torch.float32)
+        return self.norm(x)
 
 
 class PatchMerging2D(nn.Module):
@@ -56,6 +60,9 @@ class PatchMerging2D(nn.Module):
         h2, w2 = H // 2, W // 2
         quads = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
         x = torch.cat(quads, dim=-1).view(B, h2, w2, 4 * C)
+        if ops.fast_layernorm_ok(x, self.norm):
+            return self.reduction(ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps,
+                                                out_dtype=ops.autocast_dtype(x.dtype)))
         return self.reduction(self.norm(x))
 
 
@@ -227,7 +234,12 @@ class SS_Conv_SSM(nn.Module):
 
     def forward(self, input: torch.Tensor):
         left, right = input.chunk(2, dim=-1)
-        ssm = self.drop_path(self.self_attention(self.ln_1(right)))
+        if ops.fast_layernorm_ok(right, self.ln_1):
+            normed = ops.layernorm(right, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps,
+                                   out_dtype=ops.autocast_dtype(right.dtype))
+        else:
+            normed = self.ln_1(right)
+        ssm = self.drop_path(self.self_attention(normed))
         # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
         left = self.conv33conv33conv11(left.permute(0, 3, 1, 2))
         left = left.permute(0, 2, 3, 1)

@@ -105,6 +105,38 @@ def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
     return (out, merged) if want_merged else out
 
 
+def layernorm(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torch.Tensor:
+    """LayerNorm over the last dim of a channels-last (B, H, W, C) view (inference; no autograd)."""
+    dev = require_cuda(x, weight, bias)
+    B, H, W, C = x.shape
+    xv, px, _ = _token_view(x)
+    out = torch.empty((B, H, W, C), dtype=out_dtype or x.dtype, device=dev)
+    g = weight.detach().float().contiguous()
+    bt = bias.detach().float().contiguous()
+    with torch.cuda.device(dev), timed_launch("layernorm_fwd", f"B={B},L={H * W},C={C}"):
+        st = lib().mmb_layernorm_fwd(ptr(xv), ptr(g), ptr(bt), ptr(out), i64(B * H * W), _c_int(C), i64(px),
+                                     ctypes.c_float(eps), _c_int(dtype_code(xv)), _c_int(dtype_code(out)), stream_ptr(dev))
+    check(st, "mmb_layernorm_fwd")
+    return out
+
+
+def fast_layernorm_ok(x: torch.Tensor, ln) -> bool:
+    """The hand-written LayerNorm applies: CUDA, no autograd, plain affine nn.LayerNorm over C % 4 == 0 <= 2048."""
+    return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine
+            and ln.bias is not None and len(ln.normalized_shape) == 1 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048
+            and x.dtype in (torch.float32, torch.bfloat16)
+            and not needs_autograd(x, ln.weight, ln.bias))
+
+
+def autocast_dtype(default):
+    """dtype a following Linear would cast its input to (so the norm can emit it directly)."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        if dt == torch.bfloat16:
+            return dt
+    return default
+
+
 def _token_view(t: torch.Tensor, uniform_batch: bool = True):
     """(B, H, W, C) as a token matrix: returns (tensor, pixel_stride, batch_stride) with channel stride 1
     and rows h, w at a uniform pixel pitch (a dense copy is made otherwise).  Strides of size-1

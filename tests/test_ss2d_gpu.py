@@ -205,3 +205,19 @@ def test_vssm_t_bf16_top1_matches():
     rel = (logits - g["logits"]).abs().max().item() / g["logits"].abs().max().item()
     print("bf16 config-1 rel err", rel)
     assert rel < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,strided", [(2, 5, 7, 48, True), (1, 3, 3, 96, False), (2, 14, 14, 384, True),
+                                               (1, 4, 4, 1536, False), (3, 2, 9, 8, True)])
+def test_layernorm_kernel(B, H, W, C, strided):
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    full = torch.randn(B, H, W, 2 * C if strided else C, generator=g) * 3 + 1
+    x = full[..., C:] if strided else full
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    want = F.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-5)
+    got = ops.layernorm(full.cuda()[..., C:] if strided else full.cuda(), w.cuda(), b.cuda(), 1e-5)
+    assert_close(got, want, 1e-5, 1e-5, "layernorm")
+    got16 = ops.layernorm(full.cuda()[..., C:] if strided else full.cuda(), w.cuda(), b.cuda(), 1e-5, out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    assert (got16.float().cpu() - want).abs().max().item() < 0.05 * max(1.0, want.abs().max().item())
