@@ -49,8 +49,8 @@ struct CoreFwdParams {
     int NBmax;
 };
 
-template <int S, int RP, typename xc_t>
-__global__ void __launch_bounds__(384)
+template <int S, int RP, typename xc_t, int MB>
+__global__ void __launch_bounds__(S == 1 ? 256 : 384, MB)
 ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
                      const CoreFwdParams p) {
@@ -152,6 +152,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
         if (p.dbg & 1) { while (!mbar_try_wait(&full[s], ph)) {} } else mbar_wait(&full[s], ph);
 
+        const bool single_col = nwbox == 1;     // slot / position are then affine in the step index: no shuffles
         // One group = four consecutive steps.  FULL groups carry no per-step validity predicates.
         auto group = [&](auto full_tag, const int g0) {
             constexpr bool FULL = decltype(full_tag)::value;
@@ -162,8 +163,8 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 const int tl = g0 + i;
                 ok[i] = FULL || tl < nsteps;
                 const int ti = ok[i] ? (rev ? nsteps - 1 - tl : tl) : 0;
-                slot[i] = __shfl_sync(0xffffffffu, slot_l, ti);
-                pos[i] = __shfl_sync(0xffffffffu, pos_l, ti);
+                if (single_col) { slot[i] = ti; pos[i] = pbase + ti * psh; }
+                else { slot[i] = __shfl_sync(0xffffffffu, slot_l, ti); pos[i] = __shfl_sync(0xffffffffu, pos_l, ti); }
             }
             float uu[4];
 #pragma unroll
@@ -177,7 +178,8 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 else {
                     const int tl = g0 + q + S * m;
                     okk = FULL || tl < nsteps;
-                    sl = __shfl_sync(0xffffffffu, slot_l, okk ? (rev ? nsteps - 1 - tl : tl) : 0);
+                    const int ti = okk ? (rev ? nsteps - 1 - tl : tl) : 0;
+                    sl = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
                 }
                 const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
                 float acc0 = bias, acc1 = 0.f;
@@ -196,27 +198,36 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 dl[i] = S == 1 ? down[i / S] : __shfl_sync(0xffffffffu, down[i / S], lane_base + (i % S));
                 du[i] = dl[i] * uu[i];
             }
+            // Per step, in explicit phases so that the shared-memory latency is paid once per step and not once
+            // per state pair: (1) all B / C vectors of the step, (2) all exponents and inputs, (3) all exps,
+            // (4) state update, (5) y with two independent accumulator pairs.
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4* bp = reinterpret_cast<const float4*>(ps + slot[i] * CP) + q;
-                const float4* cp = bp + 4;
-                float ye = 0.f, yo = 0.f;
+                float4 bv[NS / 4], cv[NS / 4];
+#pragma unroll
+                for (int j4 = 0; j4 < NS / 4; ++j4) { bv[j4] = bp[j4 * S]; cv[j4] = bp[4 + j4 * S]; }
+                float x[NS], w[NS];
 #pragma unroll
                 for (int j4 = 0; j4 < NS / 4; ++j4) {
-                    const float4 bv = bp[j4 * S], cv = cp[j4 * S];
                     const int j = j4 * 4;
-                    float x0, x1, x2, x3, w0, w1, w2, w3;
-                    mul2(x0, x1, dl[i], dl[i], Ap[j + 0], Ap[j + 1]);
-                    mul2(x2, x3, dl[i], dl[i], Ap[j + 2], Ap[j + 3]);
-                    mul2(w0, w1, du[i], du[i], bv.x, bv.y);
-                    mul2(w2, w3, du[i], du[i], bv.z, bv.w);
-                    const float a0 = ex2_approx(x0), a1 = ex2_approx(x1), a2 = ex2_approx(x2), a3 = ex2_approx(x3);
-                    fma2(h[j + 0], h[j + 1], a0, a1, h[j + 0], h[j + 1], w0, w1);
-                    fma2(h[j + 2], h[j + 3], a2, a3, h[j + 2], h[j + 3], w2, w3);
-                    fma2(ye, yo, h[j + 0], h[j + 1], cv.x, cv.y, ye, yo);
-                    fma2(ye, yo, h[j + 2], h[j + 3], cv.z, cv.w, ye, yo);
+                    mul2(x[j + 0], x[j + 1], dl[i], dl[i], Ap[j + 0], Ap[j + 1]);
+                    mul2(x[j + 2], x[j + 3], dl[i], dl[i], Ap[j + 2], Ap[j + 3]);
+                    mul2(w[j + 0], w[j + 1], du[i], du[i], bv[j4].x, bv[j4].y);
+                    mul2(w[j + 2], w[j + 3], du[i], du[i], bv[j4].z, bv[j4].w);
                 }
-                y[i] = ye + yo;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) x[j] = ex2_approx(x[j]);
+                float ye[2] = {0.f, 0.f}, yo[2] = {0.f, 0.f};
+#pragma unroll
+                for (int j4 = 0; j4 < NS / 4; ++j4) {
+                    const int j = j4 * 4;
+                    fma2(h[j + 0], h[j + 1], x[j + 0], x[j + 1], h[j + 0], h[j + 1], w[j + 0], w[j + 1]);
+                    fma2(h[j + 2], h[j + 3], x[j + 2], x[j + 3], h[j + 2], h[j + 3], w[j + 2], w[j + 3]);
+                    fma2(ye[0], yo[0], h[j + 0], h[j + 1], cv[j4].x, cv[j4].y, ye[0], yo[0]);
+                    fma2(ye[1], yo[1], h[j + 2], h[j + 3], cv[j4].z, cv[j4].w, ye[1], yo[1]);
+                }
+                y[i] = (ye[0] + yo[0]) + (ye[1] + yo[1]);
             }
 #pragma unroll
             for (int off = S / 2; off > 0; off >>= 1) {
@@ -293,12 +304,12 @@ static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, bool train,
     return pl.smem <= 200 * 1024;
 }
 
-template <int S, int RP, typename xc_t>
+template <int S, int RP, typename xc_t, int MB = 1>
 static int launch_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
     constexpr int CP = 32 + RP;
     constexpr uint64_t XE = sizeof(xc_t);
     const CUtensorMapDataType xdt = XE == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    auto kern = ss2d_core_fwd_kernel<S, RP, xc_t>;
+    auto kern = ss2d_core_fwd_kernel<S, RP, xc_t, MB>;
     static int regs = 0;
     if (regs == 0) {
         cudaFuncAttributes fa;
@@ -343,7 +354,12 @@ static int launch_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const flo
 template <int RP, typename xc_t>
 static int dispatch_core_s(CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
     switch (pl.S) {
-        case 1: return launch_core<1, RP, xc_t>(pl, p, xc, proj, st);
+        case 1: {
+            static const int mb = getenv("MMB_CORE_MB") ? atoi(getenv("MMB_CORE_MB")) : 2;
+            if (mb == 3) return launch_core<1, RP, xc_t, 3>(pl, p, xc, proj, st);
+            if (mb == 1) return launch_core<1, RP, xc_t, 1>(pl, p, xc, proj, st);
+            return launch_core<1, RP, xc_t, 2>(pl, p, xc, proj, st);
+        }
         case 2: return launch_core<2, RP, xc_t>(pl, p, xc, proj, st);
         default: return launch_core<4, RP, xc_t>(pl, p, xc, proj, st);
     }
