@@ -261,10 +261,10 @@ struct CorePlan {
 // Lanes per channel (S) and channels per CTA (CT): enough warps to fill the machine, CTAs of at
 // most 384 threads, TMA boxes of at most 256 channels.
 static bool plan_core_tiles(int B, int D, CorePlan& pl) {
+    // Measured (profiles/README.md, S sweep): one lane per channel wins as soon as there are ~3 warps of rows
+    // per SM; below that the launch is latency-bound and splitting the 16 states over 4 lanes helps.
     const long rows = 4L * B * D;
-    const long want = 32L * 12 * num_sms();
-    int S = 1;
-    while (S < 4 && rows * S < want) S *= 2;
+    int S = rows >= 32L * 3 * num_sms() ? 1 : 4;
     if (const char* e = getenv("MMB_CORE_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int gran = 32 / S;                          // channels per warp
     int capc = 256 < 384 / S ? 256 : 384 / S;
