@@ -219,16 +219,21 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     peak, peak_src = measured_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "core_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{args.dtype},{B}")
     roof = None
     key = next((k for k in kstats if k.startswith("ss2d_core_fwd") and "L=3136" in k), None)
     if key:
         st = kstats[key]
         D, R, N, K, L = 96, 3, 16, 4, 3136
-        alg_bytes = 4 * B * L * (2 * D + K * (R + 2 * N))
+        es_x = 2 if args.dtype == "bf16" else 4           # xc element size; proj and ydir are fp32
+        alg_bytes = B * L * (D * es_x + D * 4 + 4 * K * (R + 2 * N))
         exps = B * K * D * L * N
         ach = alg_bytes / (st["avg_ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "kernel": key, "avg_ms": round(st["avg_ms"], 4), "launches": st["count"],
+                "traffic": traffic, "kernel": key, "avg_ms": round(st["avg_ms"], 4), "launches": st["count"],
                 "peak_source": peak_src,
                 "alu": {"bound": "mufu_ex2", "achieved_gexp_s": round(exps / (st["avg_ms"] * 1e-3) / 1e9, 1),
                         "peak_gexp_s": round(MUFU_EXP_PER_S / 1e9, 1),
