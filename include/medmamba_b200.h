@@ -157,6 +157,12 @@ int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, const void* 
 int mmb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* out, int64_t tokens, int D,
                       int64_t x_pixel_stride, float eps, int in_dtype, int out_dtype, void* stream);
 
+/* out[tok, c] = x[tok, c] * scale[c] + shift[c]: the eval-mode BatchNorm that opens the CNN branch
+ * (MedMamba.py:338, :352-353) fused with the gather of the strided left half and the cast to the conv dtype.
+ *   x : (tokens, C) view, channel stride 1, pixel stride x_pixel_stride;  out: (tokens, C) dense.  C % 4 == 0. */
+int mmb_affine_cast_fwd(const void* x, const float* scale, const float* shift, void* out, int64_t tokens, int C,
+                        int64_t x_pixel_stride, int in_dtype, int out_dtype, void* stream);
+
 /* ---- backward of the fused path (training; loss.backward(), train.py:284).  Parameter gradients come back
  * as per-CTA / per-batch partials that the caller sums over the leading axis: no float atomics, results are
  * bit-reproducible. ---- */

@@ -183,6 +183,27 @@ layernorm_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ gamma
 }
 
 // ------------------------------------------------------------------------------------------------
+// out[tok, c] = x[tok, c] * scale[c] + shift[c] on a strided channels-last view -> dense: the eval-mode BatchNorm
+// that opens the CNN branch (MedMamba.py:338), fused with the gather of the left half of the residual stream
+// and the cast to the convolution's dtype.
+template <typename in_t, typename out_t>
+__global__ void __launch_bounds__(256)
+affine_cast_kernel(const in_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   out_t* __restrict__ out, int64_t tokens, int C, int64_t x_pix) {
+    const int C4 = C / 4;
+    const int64_t total = tokens * C4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        const int64_t tok = idx / C4;
+        const float4 v = load4<in_t>(x + tok * x_pix + 4 * c4);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+        store4<out_t>(out + tok * C + 4 * c4,
+                      make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
 // (torch.cat + channel_shuffle(groups=2) + residual).  A thread produces 8 output channels.
 template <typename TB, typename T>   // TB: branch dtype (left, ssm); T: residual stream dtype (inp, out)
@@ -339,6 +360,31 @@ extern "C" int mmb_layernorm_fwd(const void* x, const float* gamma, const float*
     if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_LN_V(__nv_bfloat16, float);
 #undef MMB_LN_V
 #undef MMB_LN
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_affine_cast_fwd(const void* x, const float* scale, const float* shift, void* out, int64_t tokens, int C,
+                                   int64_t x_pixel_stride, int in_dtype, int out_dtype, void* stream) {
+    using namespace mmb;
+    if (!x || !scale || !shift || !out) return MMB_ERR_INVALID_ARG;
+    if (tokens < 0 || C <= 0) return MMB_ERR_INVALID_ARG;
+    if (C % 4 != 0 || x_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    if (tokens == 0) return MMB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(tokens * (C / 4), 256);
+#define MMB_AC(TI, TO)                                                                                           \
+    do {                                                                                                         \
+        if (!aligned_for4<TI>(x) || !aligned_for4<TO>(out)) return MMB_ERR_UNSUPPORTED;                          \
+        affine_cast_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), scale, shift,           \
+                                                        reinterpret_cast<TO*>(out), tokens, C, x_pixel_stride);  \
+        return launch_status();                                                                                  \
+    } while (0)
+    if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_AC(float, float);
+    if (in_dtype == MMB_F32 && out_dtype == MMB_BF16) MMB_AC(float, __nv_bfloat16);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16) MMB_AC(__nv_bfloat16, __nv_bfloat16);
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_AC(__nv_bfloat16, float);
+#undef MMB_AC
     return MMB_ERR_UNSUPPORTED;
 }
 

@@ -232,6 +232,47 @@ class SS_Conv_SSM(nn.Module):
             nn.ReLU(),
         )
 
+    # -- CNN branch, inference fast path -----------------------------------------------------------------
+    def _folded_cnn(self, dtype):
+        """Eval-mode BatchNorms folded away (cached): the leading BN becomes a per-channel affine applied while
+        gathering the left half (mmb_affine_cast_fwd); the two BNs that follow convolutions fold into those
+        convolutions' weights and biases exactly.  Invalidated when any parameter / buffer changes."""
+        seq = self.conv33conv33conv11
+        key = (dtype,) + tuple(t._version for m in seq for t in list(m.parameters()) + list(m.buffers()))
+        cached = getattr(self, "_cnn_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        with torch.no_grad():
+            def bn_affine(bn):
+                sc = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+                return sc, bn.bias.float() - bn.running_mean.float() * sc
+            sc0, sh0 = bn_affine(seq[0])
+            convs = []
+            for conv, bn in ((seq[1], seq[2]), (seq[4], seq[5]), (seq[7], None)):
+                w, b = conv.weight.float(), conv.bias.float()
+                if bn is not None:
+                    sc, sh = bn_affine(bn)
+                    w, b = w * sc.view(-1, 1, 1, 1), b * sc + sh
+                convs.append((w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype).contiguous(),
+                              conv.padding))
+            folded = (sc0.contiguous(), sh0.contiguous(), convs)
+        self._cnn_cache = (key, folded)
+        return folded
+
+    def _cnn_branch_fast(self, left: torch.Tensor) -> torch.Tensor:
+        dtype = ops.autocast_dtype(left.dtype)
+        sc0, sh0, convs = self._folded_cnn(dtype)
+        x = ops.affine_cast(left, sc0, sh0, dtype).permute(0, 3, 1, 2)        # NCHW shape, channels-last memory
+        with torch.autocast("cuda", enabled=False):
+            for w, b, pad in convs:
+                x = torch.cudnn_convolution_relu(x, w, b, (1, 1), pad, (1, 1), 1)
+        return x.permute(0, 2, 3, 1)
+
+    def _cnn_fast_ok(self, left: torch.Tensor) -> bool:
+        return (getattr(self, "fast_cnn", True) and left.is_cuda and not self.training and left.shape[-1] % 4 == 0
+                and left.dtype in (torch.float32, torch.bfloat16) and ops.fused_available()
+                and not ops.needs_autograd(left, *self.conv33conv33conv11.parameters()))
+
     def forward(self, input: torch.Tensor):
         left, right = input.chunk(2, dim=-1)
         if ops.fast_layernorm_ok(right, self.ln_1):
@@ -240,9 +281,11 @@ class SS_Conv_SSM(nn.Module):
         else:
             normed = self.ln_1(right)
         ssm = self.drop_path(self.self_attention(normed))
-        # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
-        left = self.conv33conv33conv11(left.permute(0, 3, 1, 2))
-        left = left.permute(0, 2, 3, 1)
+        if self._cnn_fast_ok(left):
+            left = self._cnn_branch_fast(left)
+        else:
+            # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
+            left = self.conv33conv33conv11(left.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
         if input.is_cuda and ops.fused_available():
             return ops.shuffle_cat_residual(left, ssm, input)
         return channel_shuffle(torch.cat((left, ssm), dim=-1), groups=2) + input

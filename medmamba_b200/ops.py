@@ -120,6 +120,19 @@ def layernorm(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torc
     return out
 
 
+def affine_cast(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out_dtype) -> torch.Tensor:
+    """(B, H, W, C) channels-last view -> dense x * scale[c] + shift[c] in out_dtype (inference)."""
+    dev = require_cuda(x, scale, shift)
+    B, H, W, C = x.shape
+    xv, px, _ = _token_view(x)
+    out = torch.empty((B, H, W, C), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev), timed_launch("affine_cast_fwd", f"B={B},L={H * W},C={C}"):
+        st = lib().mmb_affine_cast_fwd(ptr(xv), ptr(scale), ptr(shift), ptr(out), i64(B * H * W), _c_int(C), i64(px),
+                                       _c_int(dtype_code(xv)), _c_int(dtype_code(out)), stream_ptr(dev))
+    check(st, "mmb_affine_cast_fwd")
+    return out
+
+
 def fast_layernorm_ok(x: torch.Tensor, ln) -> bool:
     """The hand-written LayerNorm applies: CUDA, no autograd, plain affine nn.LayerNorm over C % 4 == 0 <= 2048."""
     return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine

@@ -221,3 +221,35 @@ def test_layernorm_kernel(B, H, W, C, strided):
     got16 = ops.layernorm(full.cuda()[..., C:] if strided else full.cuda(), w.cuda(), b.cuda(), 1e-5, out_dtype=torch.bfloat16)
     assert got16.dtype == torch.bfloat16
     assert (got16.float().cpu() - want).abs().max().item() < 0.05 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("dim,H,W", [(96, 14, 14), (16, 5, 7), (192, 7, 9)])
+def test_block_cnn_fast_path_matches_module_path(dim, H, W):
+    """Eval-mode block: folded-BatchNorm + fused conv-ReLU CNN branch vs the plain nn.Sequential."""
+    import medmamba_b200 as mm
+    torch.manual_seed(dim)
+    blk = mm.SS_Conv_SSM(hidden_dim=dim, norm_layer=torch.nn.LayerNorm).cuda().eval()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5)
+                m.weight.normal_(1, 0.2); m.bias.normal_(0, 0.2)
+    x = torch.randn(2, H, W, dim, device="cuda")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fast = blk(x)
+            blk.fast_cnn = False
+            slow = blk(x)
+            blk.fast_cnn = True
+            # the cache follows parameter updates
+            blk.conv33conv33conv11[1].weight.mul_(1.5)
+            fast2 = blk(x)
+            blk.fast_cnn = False
+            slow2 = blk(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert_close(fast, slow, 1e-4, 1e-5, "CNN fast path")
+    assert_close(fast2, slow2, 1e-4, 1e-5, "CNN fast path after a weight update")
+    assert not torch.allclose(fast, fast2)
