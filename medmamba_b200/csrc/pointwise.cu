@@ -15,21 +15,29 @@ template <int WS, typename in_t, typename out_t, bool ACT = true, bool FLIP = fa
 __global__ void __launch_bounds__(256)
 dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                       out_t* __restrict__ out, int B, int H, int W, int D, int64_t x_pix, int64_t x_batch) {
+    // weights transposed into shared memory once per CTA: swt[tap][D], so a thread's 4 channels are one LDS.128
+    extern __shared__ __align__(16) float swt[];
+    for (int i = threadIdx.x; i < D * 9; i += blockDim.x) {
+        const int ch = i / 9, tp = i % 9;
+        swt[(FLIP ? 8 - tp : tp) * D + ch] = __ldg(wgt + i);
+    }
+    __syncthreads();
     const int C4 = D / 4;
     const int strips = (W + WS - 1) / WS;
-    const int64_t total = (int64_t)B * H * strips * C4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        int64_t r = idx / C4;
-        const int st = (int)(r % strips); r /= strips;
-        const int h = (int)(r % H);
-        const int b = (int)(r / H);
+    // 32-bit index arithmetic: the host rejects problems with more than 2^31 work items
+    const uint32_t total = (uint32_t)B * H * strips * C4;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % (uint32_t)C4);
+        uint32_t r = idx / (uint32_t)C4;
+        const int st = (int)(r % (uint32_t)strips); r /= (uint32_t)strips;
+        const int h = (int)(r % (uint32_t)H);
+        const int b = (int)(r / (uint32_t)H);
         const int c = c4 * 4, w0 = st * WS;
         float wk[9][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-#pragma unroll
-            for (int tp = 0; tp < 9; ++tp) wk[tp][e] = __ldg(wgt + (int64_t)(c + e) * 9 + (FLIP ? 8 - tp : tp));
+        for (int tp = 0; tp < 9; ++tp) {
+            const float4 wv = *reinterpret_cast<const float4*>(swt + tp * D + c);
+            wk[tp][0] = wv.x; wk[tp][1] = wv.y; wk[tp][2] = wv.z; wk[tp][3] = wv.w;
         }
         float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
@@ -37,16 +45,26 @@ dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
 #pragma unroll
         for (int i = 0; i < WS; ++i) { acc[i][0] = bs.x; acc[i][1] = bs.y; acc[i][2] = bs.z; acc[i][3] = bs.w; }
         const in_t* xb = x + (int64_t)b * x_batch + c;
+        // All 3 x (WS + 2) neighbour loads are issued unconditionally from clamped coordinates (branches around
+        // them would serialise their latencies); out-of-image taps are zeroed afterwards.
+        float4 nb[3][WS + 2];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-            const int hy = h + dy - 1;
-            if (hy < 0 || hy >= H) continue;
+            const int hy = min(max(h + dy - 1, 0), H - 1);
 #pragma unroll
             for (int j = 0; j < WS + 2; ++j) {
-                const int wx = w0 + j - 1;
-                if (wx < 0 || wx >= W) continue;
-                const float4 v = load4<in_t>(xb + ((int64_t)hy * W + wx) * x_pix);
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+                const int wx = min(max(w0 + j - 1, 0), W - 1);
+                nb[dy][j] = load4<in_t>(xb + ((int64_t)hy * W + wx) * x_pix);
+            }
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const bool hok = (h + dy - 1 >= 0) && (h + dy - 1 < H);
+#pragma unroll
+            for (int j = 0; j < WS + 2; ++j) {
+                const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
+                const float vv[4] = {ok ? nb[dy][j].x : 0.f, ok ? nb[dy][j].y : 0.f, ok ? nb[dy][j].z : 0.f,
+                                     ok ? nb[dy][j].w : 0.f};
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const int i = j - dx;          // output pixel this input contributes to with tap (dy, dx)
@@ -191,10 +209,10 @@ __global__ void __launch_bounds__(256)
 affine_cast_kernel(const in_t* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                    out_t* __restrict__ out, int64_t tokens, int C, int64_t x_pix) {
     const int C4 = C / 4;
-    const int64_t total = tokens * C4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        const int64_t tok = idx / C4;
+    const uint32_t total = (uint32_t)tokens * C4;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % (uint32_t)C4);
+        const int64_t tok = idx / (uint32_t)C4;
         const float4 v = load4<in_t>(x + tok * x_pix + 4 * c4);
         const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
         const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
@@ -212,10 +230,10 @@ shuffle_cat_residual_kernel(const TB* __restrict__ left, const TB* __restrict__ 
                             T* __restrict__ out, int64_t tokens, int c, int64_t left_pix, int64_t ssm_pix,
                             int64_t inp_pix) {
     const int C4 = c / 4;
-    const int64_t total = tokens * C4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % C4);
-        const int64_t tok = idx / C4;
+    const uint32_t total = (uint32_t)tokens * C4;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % (uint32_t)C4);
+        const int64_t tok = idx / (uint32_t)C4;
         const float4 l = load4<TB>(left + tok * left_pix + 4 * c4);
         const float4 s = load4<TB>(ssm + tok * ssm_pix + 4 * c4);
         const float4 i0 = load4<T>(inp + tok * inp_pix + 8 * c4);
@@ -246,17 +264,18 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
     using namespace mmb;
     if (!x || !weight || !out) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
-    if (D % 4 != 0 || x_pixel_stride % 4 != 0 || x_batch_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if (D % 4 != 0 || D > 1280 || x_pixel_stride % 4 != 0 || x_batch_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
     if (bias && reinterpret_cast<uintptr_t>(bias) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     constexpr int WS = 4;
     const int64_t items = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 4);
+    if (items >= (1LL << 31)) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(items, 256);
 #define MMB_DW(IN, OUT)                                                                                          \
     do {                                                                                                         \
         if (!aligned_for4<IN>(x) || !aligned_for4<OUT>(out)) return MMB_ERR_UNSUPPORTED;                         \
-        dwconv3x3_silu_kernel<WS, IN, OUT><<<grid, 256, 0, st>>>(reinterpret_cast<const IN*>(x), weight, bias,   \
+        dwconv3x3_silu_kernel<WS, IN, OUT><<<grid, 256, (size_t)D * 36, st>>>(reinterpret_cast<const IN*>(x), weight, bias,   \
             reinterpret_cast<OUT*>(out), batch, H, W, D, x_pixel_stride, x_batch_stride);                        \
         return launch_status();                                                                                  \
     } while (0)
@@ -274,21 +293,22 @@ extern "C" int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* 
     using namespace mmb;
     if (!ds || !weight || !dx) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
-    if (D % 4 != 0 || !aligned_for4<float>(ds)) return MMB_ERR_UNSUPPORTED;
+    if (D % 4 != 0 || D > 1280 || !aligned_for4<float>(ds)) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     constexpr int WS = 4;
     const int64_t items = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 4);
+    if (items >= (1LL << 31)) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(items, 256);
     if (out_dtype == MMB_F32) {
         if (!aligned_for4<float>(dx)) return MMB_ERR_UNSUPPORTED;
-        dwconv3x3_silu_kernel<WS, float, float, false, true><<<grid, 256, 0, st>>>(
+        dwconv3x3_silu_kernel<WS, float, float, false, true><<<grid, 256, (size_t)D * 36, st>>>(
             ds, weight, nullptr, reinterpret_cast<float*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
         return launch_status();
     }
     if (out_dtype == MMB_BF16) {
         if (!aligned_for4<__nv_bfloat16>(dx)) return MMB_ERR_UNSUPPORTED;
-        dwconv3x3_silu_kernel<WS, float, __nv_bfloat16, false, true><<<grid, 256, 0, st>>>(
+        dwconv3x3_silu_kernel<WS, float, __nv_bfloat16, false, true><<<grid, 256, (size_t)D * 36, st>>>(
             ds, weight, nullptr, reinterpret_cast<__nv_bfloat16*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
         return launch_status();
     }
@@ -371,6 +391,7 @@ extern "C" int mmb_affine_cast_fwd(const void* x, const float* scale, const floa
     if (C % 4 != 0 || x_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (tokens == 0) return MMB_OK;
+    if (tokens * (C / 4) >= (1LL << 31)) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(tokens * (C / 4), 256);
 #define MMB_AC(TI, TO)                                                                                           \
@@ -398,6 +419,7 @@ extern "C" int mmb_shuffle_cat_residual_fwd(const void* left, const void* ssm, c
     if (c % 4 != 0 || left_pixel_stride % 4 != 0 || ssm_pixel_stride % 4 != 0 || inp_pixel_stride % 4 != 0)
         return MMB_ERR_UNSUPPORTED;
     if (tokens == 0) return MMB_OK;
+    if (tokens * (c / 4) >= (1LL << 31)) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(tokens * (c / 4), 256);
 #define MMB_SH(TB, T)                                                                                            \
