@@ -147,17 +147,21 @@ dwconv3x3_silu_bwd_ds_kernel(const in_t* __restrict__ x, const float* __restrict
             const in_t* xb = x + (int64_t)b * x_batch + c;
             float s[4] = {bs.x, bs.y, bs.z, bs.w};
             float xn[9][4];
+            // unconditional loads from clamped coordinates (branches would serialise the nine latencies)
+            float4 nb[9];
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
+            for (int tp = 0; tp < 9; ++tp) {
+                const int hy = min(max(h + tp / 3 - 1, 0), H - 1), wx = min(max(w + tp % 3 - 1, 0), W - 1);
+                nb[tp] = load4<in_t>(xb + ((int64_t)hy * W + wx) * x_pix);
+            }
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int hy = h + dy - 1, wx = w + dx - 1;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (hy >= 0 && hy < H && wx >= 0 && wx < W) v = load4<in_t>(xb + ((int64_t)hy * W + wx) * x_pix);
-                    xn[dy * 3 + dx][0] = v.x; xn[dy * 3 + dx][1] = v.y; xn[dy * 3 + dx][2] = v.z; xn[dy * 3 + dx][3] = v.w;
+            for (int tp = 0; tp < 9; ++tp) {
+                const int hy = h + tp / 3 - 1, wx = w + tp % 3 - 1;
+                const bool ok = hy >= 0 && hy < H && wx >= 0 && wx < W;
+                xn[tp][0] = ok ? nb[tp].x : 0.f; xn[tp][1] = ok ? nb[tp].y : 0.f;
+                xn[tp][2] = ok ? nb[tp].z : 0.f; xn[tp][3] = ok ? nb[tp].w : 0.f;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) s[e] = fmaf(wk[dy * 3 + dx][e], xn[dy * 3 + dx][e], s[e]);
-                }
+                for (int e = 0; e < 4; ++e) s[e] = fmaf(wk[tp][e], xn[tp][e], s[e]);
             }
             const float4 g = __ldg(reinterpret_cast<const float4*>(dxc + pix * D + c));
             const float gg[4] = {g.x, g.y, g.z, g.w};

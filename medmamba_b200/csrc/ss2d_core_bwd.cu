@@ -139,6 +139,7 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             pbase = h0 * p.W + w0;
         }
         const int nsteps = nrows * ncols;          // <= TB
+        const bool single_col = nwbox == 1;        // slot / position affine in the step index
         int slot_l = 0, pos_l = 0;
         if (lane < nsteps) {
             const int ww = lane / nrows, hh = lane - ww * nrows;
@@ -173,7 +174,8 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             for (int m = 0; m < 2; ++m) {
                 const int tl = q + S * m;
                 const bool okk = tl < nsteps;
-                const int sl = __shfl_sync(0xffffffffu, slot_l, okk ? (rev ? nsteps - 1 - tl : tl) : 0);
+                const int ti = okk ? (rev ? nsteps - 1 - tl : tl) : 0;
+                const int sl = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
                 const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
                 float acc0 = bias, acc1 = 0.f;
 #pragma unroll
@@ -191,7 +193,8 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 dl[tl] = __shfl_sync(0xffffffffu, own_dl[tl / S], lane_base + (tl % S));
                 sg[tl] = __shfl_sync(0xffffffffu, own_sg[tl / S], lane_base + (tl % S));
                 const bool ok = tl < nsteps;
-                slot[tl] = __shfl_sync(0xffffffffu, slot_l, ok ? (rev ? nsteps - 1 - tl : tl) : 0);
+                const int ti = ok ? (rev ? nsteps - 1 - tl : tl) : 0;
+                slot[tl] = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
             }
         }
 #pragma unroll
@@ -200,12 +203,16 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             const float dlu = dl[tl] * uu;
             const float4 bv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[q];
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+            float x0, x1, x2, x3, w0, w1, w2, w3;
+            mul2(x0, x1, dl[tl], dl[tl], Ap[0], Ap[1]);
+            mul2(x2, x3, dl[tl], dl[tl], Ap[2], Ap[3]);
+            mul2(w0, w1, dlu, dlu, bb[0], bb[1]);
+            mul2(w2, w3, dlu, dlu, bb[2], bb[3]);
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                hist[tl][j] = h[j];
-                aa[tl][j] = ex2_approx(dl[tl] * Ap[j]);
-                h[j] = fmaf(aa[tl][j], h[j], dlu * bb[j]);
-            }
+            for (int j = 0; j < NS; ++j) hist[tl][j] = h[j];
+            aa[tl][0] = ex2_approx(x0); aa[tl][1] = ex2_approx(x1); aa[tl][2] = ex2_approx(x2); aa[tl][3] = ex2_approx(x3);
+            fma2(h[0], h[1], aa[tl][0], aa[tl][1], h[0], h[1], w0, w1);
+            fma2(h[2], h[3], aa[tl][2], aa[tl][3], h[2], h[3], w2, w3);
         }
         // ---- phase B: reverse recurrence --------------------------------------------------------------------
 #pragma unroll
@@ -217,23 +224,35 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             const float4 bv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[q];
             const float4 cv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[4 + q];
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
-            float adu = 0.f, adl = 0.f, v[8];
+            float adu, adl, v[8];
+            {
+                // the four states of the lane as two packed pairs (FFMA2 / FMUL2)
+                float w[4], ht[4], gt[4], hpa[4], t0[4], t1[4], ga[4], acc_u[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                const float hp = hist[tl][j], a = aa[tl][j];
-                const float ht = fmaf(a, hp, dlu * bb[j]);
-                const float gt = fmaf(dy, cc[j], gcar[j]);
-                const float hpa = hp * a;
-                v[j] = gt * dlu;
-                v[NS + j] = dy * ht;
-                adu = fmaf(gt, bb[j], adu);
-                adl = fmaf(gt, fmaf(bb[j], uu, hpa * Araw[j]), adl);
-                dA[j] = fmaf(gt * hpa, dl[tl], dA[j]);
-                gcar[j] = ok ? a * gt : gcar[j];
+                for (int j = 0; j < NS; j += 2) {
+                    mul2(w[j], w[j + 1], dlu, dlu, bb[j], bb[j + 1]);
+                    fma2(ht[j], ht[j + 1], aa[tl][j], aa[tl][j + 1], hist[tl][j], hist[tl][j + 1], w[j], w[j + 1]);
+                    fma2(gt[j], gt[j + 1], dy, dy, cc[j], cc[j + 1], gcar[j], gcar[j + 1]);
+                    mul2(hpa[j], hpa[j + 1], hist[tl][j], hist[tl][j + 1], aa[tl][j], aa[tl][j + 1]);
+                    mul2(v[j], v[j + 1], gt[j], gt[j + 1], dlu, dlu);
+                    mul2(v[NS + j], v[NS + j + 1], dy, dy, ht[j], ht[j + 1]);
+                    fma2(acc_u[0], acc_u[1], gt[j], gt[j + 1], bb[j], bb[j + 1], acc_u[0], acc_u[1]);
+                    mul2(t0[j], t0[j + 1], hpa[j], hpa[j + 1], Araw[j], Araw[j + 1]);
+                    fma2(t1[j], t1[j + 1], bb[j], bb[j + 1], uu, uu, t0[j], t0[j + 1]);
+                    fma2(acc_l[0], acc_l[1], gt[j], gt[j + 1], t1[j], t1[j + 1], acc_l[0], acc_l[1]);
+                    mul2(t0[j], t0[j + 1], gt[j], gt[j + 1], hpa[j], hpa[j + 1]);
+                    fma2(dA[j], dA[j + 1], t0[j], t0[j + 1], dl[tl], dl[tl], dA[j], dA[j + 1]);
+                    mul2(ga[j], ga[j + 1], aa[tl][j], aa[tl][j + 1], gt[j], gt[j + 1]);
+                    gcar[j] = ok ? ga[j] : gcar[j];
+                    gcar[j + 1] = ok ? ga[j + 1] : gcar[j + 1];
+                }
+                adu = acc_u[0] + acc_u[1];
+                adl = acc_l[0] + acc_l[1];
             }
             adu += __shfl_xor_sync(0xffffffffu, adu, 1); adu += __shfl_xor_sync(0xffffffffu, adu, 2);
             adl += __shfl_xor_sync(0xffffffffu, adl, 1); adl += __shfl_xor_sync(0xffffffffu, adl, 2);
-            const int pos = __shfl_sync(0xffffffffu, pos_l, ok ? (rev ? nsteps - 1 - tl : tl) : 0);
+            const int tip = ok ? (rev ? nsteps - 1 - tl : tl) : 0;
+            const int pos = single_col ? pbase + tip * psh : __shfl_sync(0xffffffffu, pos_l, tip);
             const float ddr = adl * sg[tl];                  // d(Wdt.dt_r + bias); sg = 0 on masked steps
             if (ok && cvalid && q == 0) {
                 dub[pos * gstride] = fmaf(Dd, dy, dl[tl] * adu);
