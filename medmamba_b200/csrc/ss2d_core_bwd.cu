@@ -3,17 +3,19 @@
 // the forward's (Appendix A) -- the backward of a gather by index is a scatter to the same index,
 // so "cross-merge of the per-direction du" is again just the store address.
 //
-// Same ownership and TMA ring as the forward, with the sequence walked BACKWARDS in the blocks of
-// kTrainCap = 8 steps whose end states the forward checkpointed (hsave).  Four lanes per channel,
-// four states per lane, so that a whole block of history lives in REGISTERS:
-//   phase A  from the checkpoint, re-run the 8 steps forward keeping h_{t-1} and a_t of every step
-//            (64 registers) -- the only exps of the backward;
-//   phase B  the reverse recurrence g_t = dy_t C_t + a_{t+1} g_{t+1} and all gradients, no exp.
-// dB_n / dC_n need a sum over the channels of the (batch, direction): an 8-lane transposing shuffle
-// reduction inside each warp, per-warp tiles in shared memory added in fixed order, one partial per
-// channel tile in HBM.  dA / dD are per-thread accumulators, one partial per batch element.
-// No float atomics anywhere: results are bit-reproducible.
-#include <type_traits>
+// Same ownership and TMA ring as the forward: one lane per channel with the 16 states in registers, a CTA of up
+// to three warps per (batch, direction, 96 channels), warps independent of each other (no CTA barrier in the
+// loop).  The sequence is walked BACKWARDS in the blocks of kTrainCap = 8 steps whose end states the forward
+// checkpointed (hsave).  A block is processed as two half blocks of 4 steps, second half first:
+//   pass 1   from the checkpoint, advance over the first half to get the mid-block state (no history kept);
+//   phase A  re-run the half block forward, parking h_{t-1} of every step in the warp's shared-memory history;
+//   phase B  the reverse recurrence g_t = dy_t C_t + a_{t+1} g_{t+1} and all gradients (a_t recomputed).
+// That is 2.5 forward passes of exps; the MUFU pipe has room (the cost of a backward is instructions).
+// dB_n / dC_n / d dt_r need a sum over the channels of the (batch, direction): each warp transposes its 32
+// lanes x (32 + RP) values through shared memory so that lane v owns the sum of value v, and stores one
+// partial row per 32-channel group to HBM (coalesced); the host adds the groups.  dA, dD, dWdt, d dt_bias are
+// per-thread accumulators, one partial per batch element.  No float atomics: bit-reproducible.
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "core_geom.cuh"
@@ -22,11 +24,12 @@
 namespace mmb {
 
 constexpr int kBwdStages = 3;
+constexpr int kHalf = kTrainCap / 2;      // steps per half block
 
 struct CoreBwdParams {
     const float* Wdt; const float* bias; const float* A; const float* Ds; const float* hsave;
     float* dudir;                   // (B, L, 4, D)
-    float* dproj;                   // (tiles, B, L, 4, CP): [dB_n | dC_n | d dt_r]
+    float* dproj;                   // (groups, B, L, 4, CP): [dB_n | dC_n | d dt_r], groups = ceil(D / 32)
     float* dA_part;                 // (B, 4D, N)
     float* dW_part;                 // (B, 4D, RP)
     float* dD_part; float* db_part; // (B, 4D)
@@ -34,22 +37,24 @@ struct CoreBwdParams {
     int T_row, NB_row, nw, T_col, NI_col, NO_col, cap;
 };
 
-template <int RP, typename xc_t>
-__global__ void __launch_bounds__(192, 2)
+template <int S, int RP, typename xc_t>
+__global__ void __launch_bounds__(96, S == 1 ? 3 : 5)
 ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmd_row, const __grid_constant__ CUtensorMap tmd_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
                      const CoreBwdParams p) {
-    constexpr int S = 4, NS = 4, CP = 32 + RP, TB = kTrainCap, XE = (int)sizeof(xc_t);
+    constexpr int NS = kMaxState / S, CP = 32 + RP, TB = kTrainCap, XE = (int)sizeof(xc_t);
+    constexpr int CW = 32 / S;                 // channels per warp
+    constexpr int TP = CW + 4;                 // row pitch (floats) of the transposition tile: conflict-free LDS.128
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr int RW = CP;                      // floats per step in the cross-channel reduction tiles
     const int xpad = (p.cap * p.CT * XE + 127) & ~127, dpad = (p.cap * p.CT * 4 + 127) & ~127,
-              ppad = (p.cap * CP * 4 + 127) & ~127, hpad = p.CT * kMaxState * 4;
-    const int stage_bytes = xpad + dpad + ppad + hpad;
+              ppad = (p.cap * CP * 4 + 127) & ~127;
+    const int stage_bytes = xpad + dpad + ppad;
     const int nwarps = blockDim.x >> 5;
-    float* swred = reinterpret_cast<float*>(smem_raw + kBwdStages * stage_bytes);     // [2][nwarps][TB][RW]
-    int* spos = reinterpret_cast<int*>(swred + 2 * nwarps * TB * RW);                 // [2][TB]
-    uint64_t* full = reinterpret_cast<uint64_t*>(spos + 2 * TB);
+    float* shist = reinterpret_cast<float*>(smem_raw + kBwdStages * stage_bytes);     // [nwarps][kHalf][16][32]
+    float* strn = shist + nwarps * kHalf * NS * 32;                                   // [nwarps][CP][TP]
+    float* sstp = strn + nwarps * CP * TP;                                       // [nwarps][TB][3][32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sstp + nwarps * TB * 3 * 32);
     uint64_t* empty = full + kBwdStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,23 +70,18 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         uint8_t* xs = smem_raw + s * stage_bytes;
         uint8_t* ds = xs + xpad;
         uint8_t* ps = ds + dpad;
-        uint8_t* hs = ps + ppad;
-        // checkpoint after block jb-1 = state at the start of block jb: CT x 16 floats, contiguous
-        const int hbytes = jb > 0 ? min(p.CT, p.D - c0) * kMaxState * 4 : 0;
         if (!colview) {
-            mbar_expect_tx(&full[s], p.T_row * (p.CT * (XE + 4) + CP * 4) + hbytes);
+            mbar_expect_tx(&full[s], p.T_row * (p.CT * (XE + 4) + CP * 4));
             tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
             tma_load_3d(ds, &tmd_row, &full[s], c0, blk * p.T_row, b);
             tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
         } else {
             const int o = blk / p.NI_col, i = blk % p.NI_col;
-            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * (XE + 4) + CP * 4) + hbytes);
+            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * (XE + 4) + CP * 4));
             tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
             tma_load_4d(ds, &tmd_col, &full[s], c0, o * p.nw, i * p.T_col, b);
             tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
         }
-        if (hbytes)
-            bulk_load_1d(hs, p.hsave + ((((int64_t)b * 4 + k) * p.NBmax + (jb - 1)) * p.D + c0) * kMaxState, hbytes, &full[s]);
     };
 
     if (tid == 0) {
@@ -91,33 +91,32 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     }
     __syncthreads();
 
-    const int cl = tid / S, q = tid % S;
+    const int cl = tid / S, q = tid % S;      // channel inside the tile; which 16/S states this lane owns
+    const int col = lane / S;                 // channel inside the warp
     const int c = c0 + cl;
     const bool cvalid = c < p.D;
     const int row = k * p.D + (cvalid ? c : 0);
-    const int lane_base = lane & ~(S - 1);
+    const int group = c0 / CW + warp;         // channel group of this warp: index of its dproj partial
+    const bool gvalid = group * CW < p.D;
 
-    float Ap[NS], Araw[NS], gcar[NS], dA[NS], Wd[RP], Wq[RP / 4], dWq[RP / 4];
+    float Ap[NS], gcar[NS], dA[NS], Wd[RP], dWd[RP];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        const int n = 4 * q + j;
-        Araw[j] = (cvalid && n < p.N) ? p.A[(int64_t)row * p.N + n] : 0.f;
-        Ap[j] = Araw[j] * kLog2e;
+        Ap[j] = (cvalid && q * NS + j < p.N) ? p.A[(int64_t)row * p.N + q * NS + j] * kLog2e : 0.f;
         gcar[j] = 0.f; dA[j] = 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < RP; ++r) Wd[r] = (cvalid && r < p.R) ? p.Wdt[(int64_t)row * p.R + r] : 0.f;
-    // lane q owns the dt ranks r = q, q+4, ... of its channel for dWdt and d dt_r
-#pragma unroll
-    for (int i = 0; i < RP / 4; ++i) {
-        Wq[i] = q == 0 ? Wd[4 * i] : q == 1 ? Wd[4 * i + 1] : q == 2 ? Wd[4 * i + 2] : Wd[4 * i + 3];
-        dWq[i] = 0.f;
-    }
+    for (int r = 0; r < RP; ++r) { Wd[r] = (cvalid && r < p.R) ? p.Wdt[(int64_t)row * p.R + r] : 0.f; dWd[r] = 0.f; }
     const float bias = cvalid ? p.bias[row] : 0.f;
     const float Dd = cvalid ? p.Ds[row] : 0.f;
     float dD_acc = 0.f, db_acc = 0.f;
     const int64_t gstride = 4 * (int64_t)p.D;
     float* dub = p.dudir + ((int64_t)b * p.L * 4 + k) * p.D + c;
+    float* dpb = p.dproj + (((int64_t)(gvalid ? group : 0) * p.B + b) * p.L * 4 + k) * CP + lane;
+    float* hist = shist + warp * kHalf * NS * 32 + lane;        // [tl][j] at (tl * 16 + j) * 32
+    float* trn = strn + warp * CP * TP;                         // [v][col] at v * TP + col
+    float* stp = sstp + warp * TB * 3 * 32 + lane;              // per-step delta / d softplus / u of this lane
+    const float* hck = p.hsave + (((int64_t)b * 4 + k) * p.NBmax * p.D + (cvalid ? c : 0)) * kMaxState + q * NS;   // + (jb-1) * D * 16
 
     for (int it = 0; it < NB; ++it) {
         const int s = it % kBwdStages, ph = (it / kBwdStages) & 1;
@@ -134,12 +133,12 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             pbase = blk * p.T_row; nrows = min(p.T_row, p.L - pbase); ncols = 1; nwbox = 1; psh = 1;
         } else {
             const int o = blk / p.NI_col, i = blk % p.NI_col;
-            const int w0 = o * p.nw, h0 = i * p.T_col;
-            nrows = min(p.T_col, p.H - h0); ncols = min(p.nw, p.W - w0); nwbox = p.nw; psh = p.W;
-            pbase = h0 * p.W + w0;
+            const int w0 = o * p.nw, h0i = i * p.T_col;
+            nrows = min(p.T_col, p.H - h0i); ncols = min(p.nw, p.W - w0); nwbox = p.nw; psh = p.W;
+            pbase = h0i * p.W + w0;
         }
         const int nsteps = nrows * ncols;          // <= TB
-        const bool single_col = nwbox == 1;        // slot / position affine in the step index
+        const bool single_col = nwbox == 1;
         int slot_l = 0, pos_l = 0;
         if (lane < nsteps) {
             const int ww = lane / nrows, hh = lane - ww * nrows;
@@ -149,175 +148,201 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         const xc_t* xs = reinterpret_cast<const xc_t*>(smem_raw + s * stage_bytes) + cl;
         const float* dys = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad) + cl;
         const float* ps = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad + dpad);
-        const float* hs = reinterpret_cast<const float*>(smem_raw + s * stage_bytes + xpad + dpad + ppad);
-        float* wred = swred + (it & 1) * nwarps * TB * RW + warp * TB * RW;
-        if (warp == 0 && lane < TB) {
-            const int ti = lane < nsteps ? (rev ? nsteps - 1 - lane : lane) : 0;
-            spos[(it & 1) * TB + lane] = __shfl_sync(0xffu, pos_l, ti);
-        }
         mbar_wait(&full[s], ph);
-        // state at the start of the block: the forward's checkpoint after block jb-1 (staged with the tiles)
-        float h[NS];
-        if (jb > 0 && cvalid) {
-            const float4 v = *reinterpret_cast<const float4*>(hs + cl * kMaxState + 4 * q);
-            h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
-        } else {
-            h[0] = h[1] = h[2] = h[3] = 0.f;
-        }
 
-        // ---- phase A: forward through the block (time order), history in registers ---------------------
-        int slot[TB];
-        float dl[TB], sg[TB], hist[TB][NS], aa[TB][NS];
-        {
-            float own_dl[2], own_sg[2];
+        auto slot_of = [&](const int tl) {
+            const int ti = tl < nsteps ? (rev ? nsteps - 1 - tl : tl) : 0;
+            return single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
+        };
+        auto pos_of = [&](const int tl) {
+            const int ti = tl < nsteps ? (rev ? nsteps - 1 - tl : tl) : 0;
+            return single_col ? pbase + ti * psh : __shfl_sync(0xffffffffu, pos_l, ti);
+        };
+        // state at the start of the block: the forward's checkpoint after block jb-1
+        auto load_checkpoint = [&](float (&h)[NS]) {
+            if (jb > 0 && cvalid) {
+                const float4* hp4 = reinterpret_cast<const float4*>(hck + (int64_t)(jb - 1) * p.D * kMaxState);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const int tl = q + S * m;
-                const bool okk = tl < nsteps;
-                const int ti = okk ? (rev ? nsteps - 1 - tl : tl) : 0;
-                const int sl = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
-                const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
-                float acc0 = bias, acc1 = 0.f;
-#pragma unroll
-                for (int r4 = 0; r4 < RP / 4; ++r4) {
-                    const float4 v = dtp[r4];
-                    fma2(acc0, acc1, Wd[4 * r4 + 0], Wd[4 * r4 + 1], v.x, v.y, acc0, acc1);
-                    fma2(acc0, acc1, Wd[4 * r4 + 2], Wd[4 * r4 + 3], v.z, v.w, acc0, acc1);
+                for (int j4 = 0; j4 < NS / 4; ++j4) {
+                    const float4 v = __ldg(hp4 + j4);
+                    h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
                 }
-                const float raw = acc0 + acc1;
-                own_dl[m] = okk ? softplus_f(raw) : 0.f;
-                own_sg[m] = okk ? (raw > 20.f ? 1.f : sigmoid_f(raw)) : 0.f;
-            }
+            } else {
 #pragma unroll
-            for (int tl = 0; tl < TB; ++tl) {
-                dl[tl] = __shfl_sync(0xffffffffu, own_dl[tl / S], lane_base + (tl % S));
-                sg[tl] = __shfl_sync(0xffffffffu, own_sg[tl / S], lane_base + (tl % S));
-                const bool ok = tl < nsteps;
-                const int ti = ok ? (rev ? nsteps - 1 - tl : tl) : 0;
-                slot[tl] = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
+                for (int j = 0; j < NS; ++j) h[j] = 0.f;
             }
-        }
-#pragma unroll
+        };
+        // per-step scalars of the block -> the warp's step table: delta, d softplus, u
         for (int tl = 0; tl < TB; ++tl) {
-            const float uu = tl < nsteps ? to_f<xc_t>(xs[slot[tl] * p.CT]) : 0.f;
-            const float dlu = dl[tl] * uu;
-            const float4 bv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[q];
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-            float x0, x1, x2, x3, w0, w1, w2, w3;
-            mul2(x0, x1, dl[tl], dl[tl], Ap[0], Ap[1]);
-            mul2(x2, x3, dl[tl], dl[tl], Ap[2], Ap[3]);
-            mul2(w0, w1, dlu, dlu, bb[0], bb[1]);
-            mul2(w2, w3, dlu, dlu, bb[2], bb[3]);
-#pragma unroll
-            for (int j = 0; j < NS; ++j) hist[tl][j] = h[j];
-            aa[tl][0] = ex2_approx(x0); aa[tl][1] = ex2_approx(x1); aa[tl][2] = ex2_approx(x2); aa[tl][3] = ex2_approx(x3);
-            fma2(h[0], h[1], aa[tl][0], aa[tl][1], h[0], h[1], w0, w1);
-            fma2(h[2], h[3], aa[tl][2], aa[tl][3], h[2], h[3], w2, w3);
-        }
-        // ---- phase B: reverse recurrence --------------------------------------------------------------------
-#pragma unroll
-        for (int tl = TB - 1; tl >= 0; --tl) {
             const bool ok = tl < nsteps;
-            const float uu = ok ? to_f<xc_t>(xs[slot[tl] * p.CT]) : 0.f;
-            const float dy = ok ? dys[slot[tl] * p.CT] : 0.f;
-            const float dlu = dl[tl] * uu;
-            const float4 bv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[q];
-            const float4 cv = reinterpret_cast<const float4*>(ps + slot[tl] * CP)[4 + q];
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
-            float adu, adl, v[8];
-            {
-                // the four states of the lane as two packed pairs (FFMA2 / FMUL2)
-                float w[4], ht[4], gt[4], hpa[4], t0[4], t1[4], ga[4], acc_u[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
+            const int sl = slot_of(tl);
+            const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
+            float acc0 = bias, acc1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < NS; j += 2) {
-                    mul2(w[j], w[j + 1], dlu, dlu, bb[j], bb[j + 1]);
-                    fma2(ht[j], ht[j + 1], aa[tl][j], aa[tl][j + 1], hist[tl][j], hist[tl][j + 1], w[j], w[j + 1]);
-                    fma2(gt[j], gt[j + 1], dy, dy, cc[j], cc[j + 1], gcar[j], gcar[j + 1]);
-                    mul2(hpa[j], hpa[j + 1], hist[tl][j], hist[tl][j + 1], aa[tl][j], aa[tl][j + 1]);
-                    mul2(v[j], v[j + 1], gt[j], gt[j + 1], dlu, dlu);
-                    mul2(v[NS + j], v[NS + j + 1], dy, dy, ht[j], ht[j + 1]);
-                    fma2(acc_u[0], acc_u[1], gt[j], gt[j + 1], bb[j], bb[j + 1], acc_u[0], acc_u[1]);
-                    mul2(t0[j], t0[j + 1], hpa[j], hpa[j + 1], Araw[j], Araw[j + 1]);
-                    fma2(t1[j], t1[j + 1], bb[j], bb[j + 1], uu, uu, t0[j], t0[j + 1]);
-                    fma2(acc_l[0], acc_l[1], gt[j], gt[j + 1], t1[j], t1[j + 1], acc_l[0], acc_l[1]);
-                    mul2(t0[j], t0[j + 1], gt[j], gt[j + 1], hpa[j], hpa[j + 1]);
-                    fma2(dA[j], dA[j + 1], t0[j], t0[j + 1], dl[tl], dl[tl], dA[j], dA[j + 1]);
-                    mul2(ga[j], ga[j + 1], aa[tl][j], aa[tl][j + 1], gt[j], gt[j + 1]);
-                    gcar[j] = ok ? ga[j] : gcar[j];
-                    gcar[j + 1] = ok ? ga[j + 1] : gcar[j + 1];
-                }
-                adu = acc_u[0] + acc_u[1];
-                adl = acc_l[0] + acc_l[1];
+            for (int r4 = 0; r4 < RP / 4; ++r4) {
+                const float4 v = dtp[r4];
+                fma2(acc0, acc1, Wd[4 * r4 + 0], Wd[4 * r4 + 1], v.x, v.y, acc0, acc1);
+                fma2(acc0, acc1, Wd[4 * r4 + 2], Wd[4 * r4 + 3], v.z, v.w, acc0, acc1);
             }
-            adu += __shfl_xor_sync(0xffffffffu, adu, 1); adu += __shfl_xor_sync(0xffffffffu, adu, 2);
-            adl += __shfl_xor_sync(0xffffffffu, adl, 1); adl += __shfl_xor_sync(0xffffffffu, adl, 2);
-            const int tip = ok ? (rev ? nsteps - 1 - tl : tl) : 0;
-            const int pos = single_col ? pbase + tip * psh : __shfl_sync(0xffffffffu, pos_l, tip);
-            const float ddr = adl * sg[tl];                  // d(Wdt.dt_r + bias); sg = 0 on masked steps
+            const float raw = acc0 + acc1;
+            stp[(tl * 3 + 0) * 32] = ok ? softplus_f(raw) : 0.f;
+            stp[(tl * 3 + 1) * 32] = ok ? (raw > 20.f ? 1.f : sigmoid_f(raw)) : 0.f;
+            stp[(tl * 3 + 2) * 32] = ok ? to_f<xc_t>(xs[sl * p.CT]) : 0.f;
+        }
+        // one forward step of all 16 states; `park` stores h_{t-1} into history slab `hslot`
+        auto advance = [&](float (&h)[NS], const int tl, const bool park, const int hslot) {
+            const float4* bp = reinterpret_cast<const float4*>(ps + slot_of(tl) * CP) + q * (NS / 4);
+            const float dli = stp[(tl * 3 + 0) * 32];
+            const float dlu = dli * stp[(tl * 3 + 2) * 32];
+#pragma unroll
+            for (int j4 = 0; j4 < NS / 4; ++j4) {
+                const float4 bv = bp[j4];
+                const int j = 4 * j4;
+                if (park) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hist[(hslot * NS + j + e) * 32] = h[j + e];
+                }
+                float x0, x1, x2, x3, w0, w1, w2, w3;
+                mul2(x0, x1, dli, dli, Ap[j], Ap[j + 1]);
+                mul2(x2, x3, dli, dli, Ap[j + 2], Ap[j + 3]);
+                mul2(w0, w1, dlu, dlu, bv.x, bv.y);
+                mul2(w2, w3, dlu, dlu, bv.z, bv.w);
+                const float a0 = ex2_approx(x0), a1 = ex2_approx(x1), a2 = ex2_approx(x2), a3 = ex2_approx(x3);
+                fma2(h[j], h[j + 1], a0, a1, h[j], h[j + 1], w0, w1);
+                fma2(h[j + 2], h[j + 3], a2, a3, h[j + 2], h[j + 3], w2, w3);
+            }
+        };
+        // reverse step tl, history slab hslot
+        auto reverse = [&](const int tl, const int hslot) {
+            const bool ok = tl < nsteps;
+            const int sl = slot_of(tl);
+            const float4* bp = reinterpret_cast<const float4*>(ps + sl * CP) + q * (NS / 4);
+            const float dy = ok ? dys[sl * p.CT] : 0.f;
+            const float dli = stp[(tl * 3 + 0) * 32], sgi = stp[(tl * 3 + 1) * 32], u = stp[(tl * 3 + 2) * 32];
+            const float dlu = dli * u;
+            float adu[2] = {0.f, 0.f}, adA[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j4 = 0; j4 < NS / 4; ++j4) {
+                const float4 bv = bp[j4], cv = bp[4 + j4];
+                const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
+                const int j = 4 * j4;
+                float hp[4], a[4], x[4];
+                mul2(x[0], x[1], dli, dli, Ap[j], Ap[j + 1]);
+                mul2(x[2], x[3], dli, dli, Ap[j + 2], Ap[j + 3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hp[e] = hist[(hslot * NS + j + e) * 32]; a[e] = ex2_approx(x[e]); }
+#pragma unroll
+                for (int e = 0; e < 4; e += 2) {
+                    float w0, w1, ht0, ht1, gt0, gt1, hpa0, hpa1, vb0, vb1, vc0, vc1, t0, t1, ga0, ga1;
+                    mul2(w0, w1, dlu, dlu, bb[e], bb[e + 1]);
+                    fma2(ht0, ht1, a[e], a[e + 1], hp[e], hp[e + 1], w0, w1);                  // h_t
+                    fma2(gt0, gt1, dy, dy, cc[e], cc[e + 1], gcar[j + e], gcar[j + e + 1]);    // g_t
+                    mul2(hpa0, hpa1, hp[e], hp[e + 1], a[e], a[e + 1]);
+                    mul2(vb0, vb1, gt0, gt1, dlu, dlu);                                        // dB_n of this channel
+                    mul2(vc0, vc1, dy, dy, ht0, ht1);                                          // dC_n of this channel
+                    fma2(adu[0], adu[1], gt0, gt1, bb[e], bb[e + 1], adu[0], adu[1]);          // sum_n g B
+                    mul2(t0, t1, gt0, gt1, hpa0, hpa1);                                        // g h_{t-1} a
+                    fma2(adA[0], adA[1], t0, t1, Ap[j + e], Ap[j + e + 1], adA[0], adA[1]);
+                    fma2(dA[j + e], dA[j + e + 1], t0, t1, dli, dli, dA[j + e], dA[j + e + 1]);
+                    mul2(ga0, ga1, a[e], a[e + 1], gt0, gt1);
+                    gcar[j + e] = ok ? ga0 : gcar[j + e];
+                    gcar[j + e + 1] = ok ? ga1 : gcar[j + e + 1];
+                    trn[(q * NS + j + e) * TP + col] = vb0; trn[(q * NS + j + e + 1) * TP + col] = vb1;
+                    trn[(16 + q * NS + j + e) * TP + col] = vc0; trn[(16 + q * NS + j + e + 1) * TP + col] = vc1;
+                }
+            }
+            float su = adu[0] + adu[1], sa = adA[0] + adA[1];
+#pragma unroll
+            for (int off = S / 2; off > 0; off >>= 1) {      // the S lanes of a channel hold disjoint states
+                su += __shfl_xor_sync(0xffffffffu, su, off);
+                sa += __shfl_xor_sync(0xffffffffu, sa, off);
+            }
+            // d delta = sum_n g (B u + h_{t-1} a A_n);  Ap = A log2(e), so the A part is scaled back by ln 2
+            const float ddl = fmaf(su, u, sa * kLn2);
+            const float ddr = ddl * sgi;                                  // 0 on masked steps (sg = 0)
+            const int pos = pos_of(tl);
             if (ok && cvalid && q == 0) {
-                dub[pos * gstride] = fmaf(Dd, dy, dl[tl] * adu);
-                dD_acc = fmaf(dy, uu, dD_acc);
+                dub[pos * gstride] = fmaf(Dd, dy, dli * su);
+                dD_acc = fmaf(dy, u, dD_acc);
             }
             db_acc += ddr;
-            // dWdt[c][r] += ddr * dt_r and d dt_r += Wdt[c][r] * ddr (summed over the warp's 8 channels)
+            const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
 #pragma unroll
-            for (int i = 0; i < RP / 4; ++i) {
-                const float dtv = ps[slot[tl] * CP + 32 + q + 4 * i];
-                dWq[i] = fmaf(ddr, dtv, dWq[i]);
-                float w = Wq[i] * ddr;
-                w += __shfl_xor_sync(0xffffffffu, w, 4);
-                w += __shfl_xor_sync(0xffffffffu, w, 8);
-                w += __shfl_xor_sync(0xffffffffu, w, 16);
-                if (lane < 4) wred[tl * RW + 32 + q + 4 * i] = w;
-            }
-            // sum v[0..7] over the 8 channels of this warp (lanes with equal q)
+            for (int r4 = 0; r4 < RP / 4; ++r4) {
+                const float4 v = dtp[r4];
+                const float dt4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                const bool hi = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < half; ++i) {
-                    const float send = hi ? v[i] : v[i + half];
-                    const float keep = hi ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int e = 0; e < 4; ++e) {
+                    dWd[4 * r4 + e] = fmaf(ddr, dt4[e], dWd[4 * r4 + e]);
+                    if (q == 0) trn[(32 + 4 * r4 + e) * TP + col] = Wd[4 * r4 + e] * ddr;
                 }
             }
+            __syncwarp();
+            // lane v sums row v over the warp's channels: [0,16) dB_n, [16,32) dC_n; rows 32.. are d dt_r
             {
-                const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
-                const int n = 4 * q + (idx & 3);
-                wred[tl * RW + (idx < 4 ? n : 16 + n)] = v[0];
+                const float4* rowp = reinterpret_cast<const float4*>(trn + lane * TP);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CW / 4; ++i) { const float4 v = rowp[i]; s0 += v.x + v.y; s1 += v.z + v.w; }
+                if (ok && gvalid) dpb[(int64_t)pos * 4 * CP] = s0 + s1;
+                if (lane < RP) {
+                    const float4* rowq = reinterpret_cast<const float4*>(trn + (32 + lane) * TP);
+                    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < CW / 4; ++i) { const float4 v = rowq[i]; q0 += v.x + v.y; q1 += v.z + v.w; }
+                    if (ok && gvalid) dpb[(int64_t)pos * 4 * CP + 32] = q0 + q1;
+                }
             }
-        }
+            __syncwarp();
+        };
+
+        float h[NS];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);     // the stage's tiles are no longer needed
-        __syncthreads();
-        // ---- this channel tile's partial dB / dC of the block, warps added in fixed order ---------------
-        {
-            const float* wr = swred + (it & 1) * nwarps * TB * RW;
-            float* out = p.dproj + (((int64_t)tile * p.B + b) * p.L * 4 + k) * RW;
-            for (int idx = tid; idx < nsteps * RW; idx += blockDim.x) {
-                const int tl = idx / RW, vv = idx - tl * RW;
-                float sum = 0.f;
-                for (int w = 0; w < nwarps; ++w) sum += wr[(w * TB + tl) * RW + vv];
-                out[(int64_t)spos[(it & 1) * TB + tl] * 4 * RW + vv] = sum;
-            }
+        if (nsteps > kHalf) {
+            // second half first: pass 1 over the first half, then phase A / B on steps kHalf .. TB-1
+            load_checkpoint(h);
+            for (int tl = 0; tl < kHalf; ++tl) advance(h, tl, false, 0);
+            for (int tl = kHalf; tl < TB; ++tl) advance(h, tl, true, tl - kHalf);
+            __syncwarp();
+            for (int tl = TB - 1; tl >= kHalf; --tl) reverse(tl, tl - kHalf);
         }
+        // first half
+        load_checkpoint(h);
+        for (int tl = 0; tl < kHalf; ++tl) advance(h, tl, true, tl);
+        __syncwarp();
+        for (int tl = kHalf - 1; tl >= 0; --tl) reverse(tl, tl);
+
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
     if (cvalid) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            const int n = 4 * q + j;
-            if (n < p.N) p.dA_part[((int64_t)b * 4 * p.D + row) * p.N + n] = dA[j];
-        }
-#pragma unroll
-        for (int i = 0; i < RP / 4; ++i) p.dW_part[((int64_t)b * 4 * p.D + row) * RP + q + 4 * i] = dWq[i];
+        for (int j = 0; j < NS; ++j)
+            if (q * NS + j < p.N) p.dA_part[((int64_t)b * 4 * p.D + row) * p.N + q * NS + j] = dA[j];
         if (q == 0) {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) p.dW_part[((int64_t)b * 4 * p.D + row) * RP + r] = dWd[r];
             p.dD_part[(int64_t)b * 4 * p.D + row] = dD_acc;
             p.db_part[(int64_t)b * 4 * p.D + row] = db_acc;
         }
     }
 }
 
-template <int RP, typename xc_t>
+// lanes per channel: 2 unless the launch has many more warps than the machine holds (thin warps hide the
+// latency of the reverse step better; S = 1 has the fewest instructions)
+static int core_bwd_split(int B, int D) {
+    if (const char* e = getenv("MMB_BWD_S")) { const int v = atoi(e); if (v == 1 || v == 2) return v; }
+    return (4L * B * D >= 32L * 40 * num_sms()) ? 1 : 2;
+}
+// channels per CTA: one warp per 32/S-channel group, up to three warps, chosen to divide the group count
+static int core_bwd_ct(int D, int S) {
+    const int cw = 32 / S;
+    const int groups = (D + cw - 1) / cw;
+    const int per = groups % 3 == 0 ? 3 : (groups % 2 == 0 ? 2 : (groups <= 3 ? groups : 1));
+    return per * cw;
+}
+
+template <int S, int RP, typename xc_t>
 static int launch_core_bwd(CoreBwdParams& p, const void* xc, const float* dY, const float* proj, cudaStream_t st) {
     constexpr int CP = 32 + RP;
     constexpr uint64_t XE = sizeof(xc_t);
@@ -348,12 +373,12 @@ static int launch_core_bwd(CoreBwdParams& p, const void* xc, const float* dY, co
         const uint32_t box[5] = {CP, 1, (uint32_t)p.nw, (uint32_t)p.T_col, 1};
         if (!make_tmap(&tmp_col, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, proj, dims, str, box)) return MMB_ERR_UNSUPPORTED;
     }
-    const int threads = p.CT * 4, nwarps = threads / 32;
+    const int threads = p.CT * S, nwarps = threads / 32;
     const size_t xpad = ((size_t)p.cap * p.CT * XE + 127) & ~(size_t)127, dpad = ((size_t)p.cap * p.CT * 4 + 127) & ~(size_t)127,
-                 ppad = ((size_t)p.cap * CP * 4 + 127) & ~(size_t)127, hpad = (size_t)p.CT * kMaxState * 4;
-    const size_t smem = kBwdStages * (xpad + dpad + ppad + hpad) + (size_t)2 * nwarps * kTrainCap * CP * 4 + 2 * kTrainCap * 4 +
+                 ppad = ((size_t)p.cap * CP * 4 + 127) & ~(size_t)127;
+    const size_t smem = kBwdStages * (xpad + dpad + ppad) + (size_t)nwarps * (kHalf * (kMaxState / S) * 32 + CP * (32 / S + 4) + kTrainCap * 3 * 32) * 4 +
                         2 * kBwdStages * sizeof(uint64_t);
-    auto kern = ss2d_core_bwd_kernel<RP, xc_t>;
+    auto kern = ss2d_core_bwd_kernel<S, RP, xc_t>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -363,30 +388,22 @@ static int launch_core_bwd(CoreBwdParams& p, const void* xc, const float* dY, co
 }
 
 template <typename xc_t>
-static int dispatch_core_bwd(int dt_pad, CoreBwdParams& p, const void* xc, const float* dY, const float* proj, cudaStream_t st) {
+static int dispatch_core_bwd(int S, int dt_pad, CoreBwdParams& p, const void* xc, const float* dY, const float* proj, cudaStream_t st) {
+#define MMB_BWD_CASE(RPV)                                                                       \
+    case RPV: return S == 1 ? launch_core_bwd<1, RPV, xc_t>(p, xc, dY, proj, st)                    \
+                            : launch_core_bwd<2, RPV, xc_t>(p, xc, dY, proj, st);
     switch (dt_pad) {
-        case 4: return launch_core_bwd<4, xc_t>(p, xc, dY, proj, st);
-        case 8: return launch_core_bwd<8, xc_t>(p, xc, dY, proj, st);
-        case 12: return launch_core_bwd<12, xc_t>(p, xc, dY, proj, st);
-        case 16: return launch_core_bwd<16, xc_t>(p, xc, dY, proj, st);
-        case 24: return launch_core_bwd<24, xc_t>(p, xc, dY, proj, st);
-        case 32: return launch_core_bwd<32, xc_t>(p, xc, dY, proj, st);
+        MMB_BWD_CASE(4) MMB_BWD_CASE(8) MMB_BWD_CASE(12) MMB_BWD_CASE(16) MMB_BWD_CASE(24) MMB_BWD_CASE(32)
         default: return MMB_ERR_UNSUPPORTED;
     }
-}
-
-static int core_bwd_ct(int D) {            // channels per CTA: <= 48 (192 threads, two CTAs per SM), a multiple of 8
-    const int tiles = (D + 47) / 48;
-    int ct = (D + tiles - 1) / tiles;
-    return (ct + 7) / 8 * 8;
+#undef MMB_BWD_CASE
 }
 
 }  // namespace mmb
 
 extern "C" int mmb_ss2d_core_bwd_tiles(int D) {
     if (D <= 0) return MMB_ERR_INVALID_ARG;
-    const int ct = mmb::core_bwd_ct(D);
-    return (D + ct - 1) / ct;
+    return (D + 15) / 16;                  // upper bound: one dproj partial per 16-channel group (unused ones are zero)
 }
 
 extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const float* Wdt,
@@ -410,10 +427,16 @@ extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float*
     p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds; p.hsave = hsave;
     p.dudir = dudir; p.dproj = dproj_part; p.dA_part = dA_part; p.dW_part = dW_part; p.dD_part = dD_part; p.db_part = db_part;
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank;
-    p.CT = core_bwd_ct(D); p.tiles = (D + p.CT - 1) / p.CT; p.NBmax = g.nblocks_max();
+    const int S = core_bwd_split(batch, D);
+    p.CT = core_bwd_ct(D, S); p.tiles = (D + p.CT - 1) / p.CT; p.NBmax = g.nblocks_max();
     p.T_row = g.T_row; p.NB_row = g.NB_row; p.nw = g.nw; p.T_col = g.T_col; p.NI_col = g.NI_col; p.NO_col = g.NO_col;
     p.cap = g.cap;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (xc_dtype == MMB_F32) return dispatch_core_bwd<float>(dt_pad, p, xc, dY, proj, st);
-    return dispatch_core_bwd<__nv_bfloat16>(dt_pad, p, xc, dY, proj, st);
+    // partial rows of groups this launch does not own (S = 1 uses every other 16-channel slot) must read as zero
+    if (S == 1) {
+        cudaError_t e = cudaMemsetAsync(dproj_part, 0, sizeof(float) * (size_t)((D + 15) / 16) * batch * H * W * 4 * (32 + dt_pad), st);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    if (xc_dtype == MMB_F32) return dispatch_core_bwd<float>(S, dt_pad, p, xc, dY, proj, st);
+    return dispatch_core_bwd<__nv_bfloat16>(S, dt_pad, p, xc, dY, proj, st);
 }

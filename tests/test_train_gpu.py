@@ -99,6 +99,14 @@ def test_fused_backward_matches_interface_backward(d_model, H, W, B):
         assert err < 2e-3, f"{name}: fused vs interface backward differ by {err:.2e}"
 
 
+@pytest.mark.parametrize("split", ["1", "2"])
+def test_fused_backward_both_lane_splits(split, monkeypatch):
+    """The backward kernel's one- and two-lanes-per-channel instantiations agree with the interface backward."""
+    monkeypatch.setenv("MMB_BWD_S", split)
+    test_fused_backward_matches_interface_backward(96, 12, 10, 2)
+    test_fused_backward_matches_interface_backward(40, 7, 7, 1)
+
+
 def test_fused_backward_deterministic_and_bf16():
     import medmamba_b200 as mm
     torch.manual_seed(0)
