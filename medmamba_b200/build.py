@@ -39,7 +39,7 @@ def _digest() -> str:
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(INCLUDE, "medmamba_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # location-independent: the GPU box mounts the repo elsewhere
         h.update(open(f, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -53,6 +53,20 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB_PATH
+    # one builder at a time (torchrun starts one process per GPU); the others wait and re-check
+    import fcntl
+    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    with open(os.path.join(HERE, "_build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
     procs = []
@@ -68,8 +82,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if pr.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
-    subprocess.check_call(link)
+    tmp = LIB_PATH + ".tmp"
+    subprocess.check_call([_nvcc(), "-shared", "-o", tmp] + objs + ["-lcudart"])
+    os.replace(tmp, LIB_PATH)                        # never expose a half-written library
     with open(os.path.join(HERE, "_build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
