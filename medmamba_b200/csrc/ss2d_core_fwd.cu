@@ -258,21 +258,54 @@ struct CorePlan {
     size_t smem;
 };
 
+// Channels per CTA for the one-lane-per-channel build (128 registers: 16 warps per SM at most).
+// Cost model fitted to the CT sweeps in profiles/README.md (round 1, session 2): a round of resident CTAs with
+// w warps per SM costs about 320 + 23 w cycles per step (measured at w = 6, 12, 15, 16: 460, 584, 684, 692; the
+// MUFU floor is 36 w: 18 MUFU x 8 cycles per warp-step on 4 sub-partitions), the CTAs left over after the full
+// rounds spread over the SMs, and
+// CTA shapes other than 3..5 warps carry the measured penalty (1- and 2-warp CTAs repeat the proj loads and
+// the per-block bookkeeping, 8-warp CTAs wait on their slowest warp before a stage is refilled).
+static void plan_one_lane_tiles(int B, int D, int L, int& CT, int& tiles) {
+    static const double shape_penalty[9] = {0, 1.19, 1.13, 1.02, 1.0, 1.03, 1.05, 1.08, 1.12};
+    const int sms = num_sms();
+    double best = 1e300;
+    CT = 0; tiles = 0;
+    for (int nt = 1; nt <= (D + 31) / 32; ++nt) {
+        const int ct = ((D + nt - 1) / nt + 31) / 32 * 32;
+        if (ct > 256 || (D + ct - 1) / ct != nt) continue;
+        const int wpc = ct / 32;
+        const int c = 16 / wpc;
+        const long n = 4L * B * nt, per_round = (long)sms * c;
+        const long full = n / per_round, rest = n % per_round;
+        auto round_cost = [](int warps) { return 320.0 + 23.0 * warps; };
+        double cost = full * round_cost(c * wpc);
+        if (rest) cost += round_cost((int)((rest + sms - 1) / sms) * wpc);
+        cost *= shape_penalty[wpc] * (L + 24);
+        if (cost < best * 0.999) { best = cost; CT = ct; tiles = nt; }
+    }
+}
+
 // Lanes per channel (S) and channels per CTA (CT): enough warps to fill the machine, CTAs of at
 // most 384 threads, TMA boxes of at most 256 channels.
-static bool plan_core_tiles(int B, int D, CorePlan& pl) {
+static bool plan_core_tiles(int B, int D, int L, CorePlan& pl) {
     // Measured (profiles/README.md, S sweep): one lane per channel wins as soon as there are ~3 warps of rows
     // per SM; below that the launch is latency-bound and splitting the 16 states over 4 lanes helps.
     const long rows = 4L * B * D;
     int S = rows >= 32L * 3 * num_sms() ? 1 : 4;
     if (const char* e = getenv("MMB_CORE_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int gran = 32 / S;                          // channels per warp
-    int capc = 256 < 384 / S ? 256 : 384 / S;
-    capc -= capc % gran;
-    int tiles = (D + capc - 1) / capc;
-    int CT = (D + tiles - 1) / tiles;
-    CT = (CT + gran - 1) / gran * gran;
-    tiles = (D + CT - 1) / CT;
+    int CT, tiles;
+    if (S == 1) {
+        plan_one_lane_tiles(B, D, L, CT, tiles);
+        if (const char* e = getenv("MMB_CORE_CT")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) { CT = v; tiles = (D + CT - 1) / CT; } }
+    } else {
+        int capc = 256 < 384 / S ? 256 : 384 / S;
+        capc -= capc % gran;
+        tiles = (D + capc - 1) / capc;
+        CT = (D + tiles - 1) / tiles;
+        CT = (CT + gran - 1) / gran * gran;
+        tiles = (D + CT - 1) / CT;
+    }
     if (CT > 256) return false;
     pl.S = S; pl.CT = CT; pl.tiles = tiles; pl.threads = CT * S;
     return true;
@@ -405,7 +438,7 @@ extern "C" int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float*
     if ((reinterpret_cast<uintptr_t>(xc) | reinterpret_cast<uintptr_t>(proj)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     CorePlan pl;
-    if (!plan_core_tiles(batch, D, pl)) return MMB_ERR_UNSUPPORTED;
+    if (!plan_core_tiles(batch, D, H * W, pl)) return MMB_ERR_UNSUPPORTED;
     CoreFwdParams p;
     p.ydir = ydir; p.Wdt = Wdt; p.bias = dt_bias; p.A = A; p.Ds = Ds; p.hsave = hsave; p.NBmax = 0;
     p.B = batch; p.H = H; p.W = W; p.L = H * W; p.D = D; p.N = dstate; p.R = dt_rank; p.CT = pl.CT;

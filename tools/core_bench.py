@@ -10,14 +10,26 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--stage", type=int, default=-1)
 ap.add_argument("--noflush", action="store_true")
+ap.add_argument("--variants", default="", help="comma list of values of the --env variable to sweep in-process")
+ap.add_argument("--env", default="MMB_CORE_CT", help="environment knob swept by --variants (read by the library per call)")
+ap.add_argument("--bf16", action="store_true", help="bf16 xc (the autocast layout)")
 args = ap.parse_args()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for si, (H, W, D, R) in enumerate(STAGES):
+cases = [(si, v) for si in range(len(STAGES)) for v in (args.variants.split(",") if args.variants else [None])]
+for si, variant in cases:
+    H, W, D, R = STAGES[si]
     if args.stage >= 0 and si != args.stage:
         continue
+    if variant is not None:
+        if variant == "default":
+            os.environ.pop(args.env, None)
+        else:
+            os.environ[args.env] = variant
     B, N = args.batch, 16
     g = torch.Generator(device="cuda").manual_seed(0)
     xc = 0.1 * torch.randn(B, H, W, D, device="cuda", generator=g)
+    if args.bf16:
+        xc = xc.bfloat16()
     rp = ops.dt_pad(R)
     proj = 0.05 * torch.randn(B, H, W, 4, 32 + rp, device="cuda", generator=g)
     Wdt = torch.randn(4, D, R, device="cuda", generator=g) * R ** -0.5
@@ -25,8 +37,12 @@ for si, (H, W, D, R) in enumerate(STAGES):
     A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(4 * D, 1).contiguous()
     Ds = torch.ones(4 * D, device="cuda")
     run = lambda: ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R)
-    for _ in range(3):
-        run()
+    try:
+        for _ in range(3):
+            run()
+    except Exception as e:      # a variant whose ring does not fit this shape
+        print(json.dumps(dict(stage=si + 1, batch=B, variant=variant, error=str(e)[:80])))
+        continue
     torch.cuda.synchronize()
     ts = []
     for _ in range(args.iters):

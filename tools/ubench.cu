@@ -60,7 +60,54 @@ void run(const char* name, double ops_per_iter, int warps_per_sm) {
     cudaFree(out);
 }
 
+// Warp -> SM sub-partition mapping: MUFU-only CTAs of `tpb` threads, `cps` CTAs per SM; prints the exp rate and
+// the histogram of %warpid % 4 on SM 0 (does a 3-warp CTA leave a sub-partition idle?).
+__global__ void kmap(float* out, int* ids, int iters, float seed) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed * i + threadIdx.x * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = ex2(a[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if ((threadIdx.x & 31) == 0) {
+        unsigned sm, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        ids[2 * w] = sm; ids[2 * w + 1] = wid;
+    }
+}
+
+void run_map(int tpb, int cps) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int grid = sms * cps, nw = grid * tpb / 32;
+    float* out; cudaMalloc(&out, sizeof(float) * grid * tpb);
+    int* ids; cudaMalloc(&ids, sizeof(int) * 2 * nw);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000;
+    kmap<<<grid, tpb>>>(out, ids, 100, 0.5f);
+    cudaEventRecord(e0);
+    kmap<<<grid, tpb>>>(out, ids, iters, 0.5f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    int* h = new int[2 * nw];
+    cudaMemcpy(h, ids, sizeof(int) * 2 * nw, cudaMemcpyDeviceToHost);
+    int hist[4] = {0, 0, 0, 0}, on0 = 0;
+    for (int w = 0; w < nw; ++w) if (h[2 * w] == 0) { hist[h[2 * w + 1] & 3]++; on0++; }
+    const double total = 16.0 * iters * (double)grid * tpb;
+    printf("map tpb=%3d ctas/SM=%2d  %.3f ms  %.2f exp/clk/SM (1965 MHz)  SM0: %d warps, warpid%%4 histogram %d %d %d %d\n",
+           tpb, cps, ms, total / ms / 1e6 / sms / 1.965e3, on0, hist[0], hist[1], hist[2], hist[3]);
+    delete[] h; cudaFree(out); cudaFree(ids);
+}
+
 int main() {
+    run_map(96, 5); run_map(96, 2); run_map(96, 7); run_map(128, 4); run_map(32, 15); run_map(32, 16);
+    run_map(192, 2); run_map(64, 8); run_map(256, 2);
     for (int w : {4, 8, 16, 32}) {
         run<0>("ffma", 16, w);
         run<3>("ffma2", 16, w);
