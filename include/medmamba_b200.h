@@ -163,6 +163,24 @@ int mmb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int mmb_affine_cast_fwd(const void* x, const float* scale, const float* shift, void* out, int64_t tokens, int C,
                         int64_t x_pixel_stride, int in_dtype, int out_dtype, void* stream);
 
+/* Patch embedding (MedMamba.py:54-76): Conv2d(3 -> embed_dim, kernel 4, stride 4) of an NCHW image batch, the
+ * NCHW -> NHWC permute and LayerNorm(embed_dim) in one pass.  Inference path; fp32 accumulation and statistics.
+ *   x      : (batch, 3, Hin, Win) dense, dtype in_dtype (fp32 or bf16), 16-byte aligned rows (Win % 4 == 0)
+ *   weight : (embed_dim, 3, 4, 4) fp32;  conv_bias: (embed_dim) fp32 or NULL;  gamma, beta: (embed_dim) fp32
+ *   out    : (batch, Hin/4, Win/4, embed_dim) fp32 dense
+ * Hin % 4 == 0, Win % 4 == 0, embed_dim % 32 == 0, embed_dim <= 128; other shapes return MMB_ERR_UNSUPPORTED. */
+int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const float* conv_bias, const float* gamma,
+                           const float* beta, float* out, int batch, int Hin, int Win, int embed_dim, float eps,
+                           int in_dtype, void* stream);
+
+/* Patch merging up to the norm (MedMamba.py:93-117): the 2x2 neighbourhood gather (x0, x1, x2, x3 = pixels
+ * (2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1)), their concatenation and LayerNorm(4C) in one pass; odd trailing
+ * rows / columns are dropped like the reference's SHAPE_FIX.  The Linear(4C -> 2C) that follows stays a GEMM.
+ *   x : (batch, H, W, C) dense channels-last;  gamma, beta: (4C) fp32;  out: (batch, H/2, W/2, 4C) dense
+ * C % 4 == 0, C <= 512. */
+int mmb_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta, void* out, int batch, int H, int W,
+                           int C, float eps, int in_dtype, int out_dtype, void* stream);
+
 /* ---- backward of the fused path (training; loss.backward(), train.py:284).  Parameter gradients come back
  * as per-CTA / per-batch partials that the caller sums over the leading axis: no float atomics, results are
  * bit-reproducible. ---- */

@@ -37,6 +37,9 @@ class PatchEmbed2D(nn.Module):
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
 
     def forward(self, x):
+        if self.norm is not None and getattr(self, "fused", True) and ops.fast_patch_embed_ok(x, self.proj, self.norm):
+            return ops.patch_embed_ln(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
+                                      self.norm.eps)
         x = self.proj(x).permute(0, 2, 3, 1)
         if self.norm is None:
             return x
@@ -57,6 +60,9 @@ class PatchMerging2D(nn.Module):
 
     def forward(self, x):
         B, H, W, C = x.shape
+        if getattr(self, "fused", True) and ops.fast_patch_merge_ok(x, self.norm):
+            return self.reduction(ops.patch_merge_ln(x, self.norm.weight, self.norm.bias, self.norm.eps,
+                                                     out_dtype=ops.autocast_dtype(x.dtype)))
         h2, w2 = H // 2, W // 2
         quads = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
         x = torch.cat(quads, dim=-1).view(B, h2, w2, 4 * C)

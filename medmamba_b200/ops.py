@@ -120,6 +120,61 @@ def layernorm(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torc
     return out
 
 
+def patch_embed_ln(x: torch.Tensor, conv_weight, conv_bias, ln_weight, ln_bias, eps: float) -> torch.Tensor:
+    """(B, 3, Hin, Win) NCHW images -> (B, Hin/4, Win/4, E) fp32 tokens: 4x4 stride-4 convolution, permute and
+    LayerNorm in one kernel (MedMamba.py:54-76; inference; no autograd)."""
+    dev = require_cuda(x, conv_weight, ln_weight, ln_bias)
+    B, Cin, Hin, Win = x.shape
+    E = conv_weight.shape[0]
+    xv = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty((B, Hin // 4, Win // 4, E), dtype=torch.float32, device=dev)
+    w = conv_weight.detach().float().contiguous()
+    cb = None if conv_bias is None else conv_bias.detach().float().contiguous()
+    g = ln_weight.detach().float().contiguous()
+    bt = ln_bias.detach().float().contiguous()
+    with torch.cuda.device(dev), timed_launch("patch_embed_ln_fwd", f"B={B},H={Hin},W={Win},E={E}"):
+        st = lib().mmb_patch_embed_ln_fwd(ptr(xv), ptr(w), ptr(cb), ptr(g), ptr(bt), ptr(out), _c_int(B), _c_int(Hin),
+                                          _c_int(Win), _c_int(E), ctypes.c_float(eps), _c_int(dtype_code(xv)),
+                                          stream_ptr(dev))
+    check(st, "mmb_patch_embed_ln_fwd")
+    return out
+
+
+def fast_patch_embed_ok(x: torch.Tensor, proj, norm) -> bool:
+    """The fused patch-embed kernel applies: CUDA, no autograd, 4x4 stride-4 conv of 3 channels, E % 32 == 0 <= 128."""
+    return (x.is_cuda and x.dim() == 4 and isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine
+            and norm.bias is not None and isinstance(proj, torch.nn.Conv2d) and proj.in_channels == 3
+            and tuple(proj.kernel_size) == (4, 4) and tuple(proj.stride) == (4, 4) and tuple(proj.padding) == (0, 0)
+            and tuple(proj.dilation) == (1, 1) and proj.groups == 1 and proj.out_channels % 32 == 0
+            and proj.out_channels <= 128 and x.shape[1] == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
+            and x.dtype in (torch.float32, torch.bfloat16)
+            and not needs_autograd(x, proj.weight, proj.bias, norm.weight, norm.bias))
+
+
+def patch_merge_ln(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torch.Tensor:
+    """(B, H, W, C) -> (B, H//2, W//2, 4C): 2x2 gather, concat and LayerNorm(4C) in one kernel
+    (MedMamba.py:93-117; inference; no autograd)."""
+    dev = require_cuda(x, weight, bias)
+    B, H, W, C = x.shape
+    xv = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty((B, H // 2, W // 2, 4 * C), dtype=out_dtype or x.dtype, device=dev)
+    g = weight.detach().float().contiguous()
+    bt = bias.detach().float().contiguous()
+    with torch.cuda.device(dev), timed_launch("patch_merge_ln_fwd", f"B={B},L={H * W},C={C}"):
+        st = lib().mmb_patch_merge_ln_fwd(ptr(xv), ptr(g), ptr(bt), ptr(out), _c_int(B), _c_int(H), _c_int(W), _c_int(C),
+                                          ctypes.c_float(eps), _c_int(dtype_code(xv)), _c_int(dtype_code(out)),
+                                          stream_ptr(dev))
+    check(st, "mmb_patch_merge_ln_fwd")
+    return out
+
+
+def fast_patch_merge_ok(x: torch.Tensor, ln) -> bool:
+    return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine
+            and ln.bias is not None and x.shape[-1] % 4 == 0 and x.shape[-1] <= 512
+            and tuple(ln.normalized_shape) == (4 * x.shape[-1],) and x.dtype in (torch.float32, torch.bfloat16)
+            and not needs_autograd(x, ln.weight, ln.bias))
+
+
 def affine_cast(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out_dtype) -> torch.Tensor:
     """(B, H, W, C) channels-last view -> dense x * scale[c] + shift[c] in out_dtype (inference)."""
     dev = require_cuda(x, scale, shift)
