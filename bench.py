@@ -9,7 +9,9 @@ per GPU -- the batch-sharded inference workload of BASELINE configs[2].  Every S
 hand-written sm_100a kernels (dwconv+SiLU, the 4-direction TMA scan, out_norm*SiLU(z), shuffle +
 residual) through the C ABI; linears and the CNN branch are torch (cuBLAS / cuDNN).
   value   : images/s with the input batch resident in HBM, K steps between CUDA events, max over ranks
-  e2e     : the same through the public call with HOST (pinned) images: H2D copy + forward + logits D2H
+  e2e     : the same through the public host-facing call (medmamba_b200.InferencePipeline) with HOST (pinned)
+            images: every step's H2D copy + forward + logits D2H inside the timed region, the copy of the next
+            batch overlapped with the forward of the current one
   roofline: the dominant kernel (ss2d_core_fwd at the stage-1 shape, L = 3136) timed live with CUDA
             events on its launch stream inside the timed steps; algorithmic bytes are the fused
             SS2D-core figure es*B*L*(2D + K(R+2N)) of SURVEY.md section 8(d).  The kernel is bound by
@@ -232,18 +234,21 @@ def run_ours(args):
     launches = timer.launches
     kstats = timer.summary()
 
-    # ---- end to end: host images -> H2D -> forward -> logits -> host -------------------------------
-    x_host = torch.randn(B, 3, RES, RES).pin_memory()
-    x_dev = torch.empty_like(x)
-    for _ in range(2):
-        x_dev.copy_(x_host, non_blocking=True); step(x_dev).float().cpu()
+    # ---- end to end: the public host-facing call (medmamba_b200.InferencePipeline): every step copies its batch
+    # from pinned host memory and reads its logits back; the copy of step i+1 overlaps the forward of step i ----
+    pipe = mm.InferencePipeline(net, autocast_dtype=torch.bfloat16 if args.dtype == "bf16" else None)
+    x_hosts = [torch.randn(B, 3, RES, RES).pin_memory() for _ in range(2)]
+    for _ in pipe.stream(x_hosts):
+        pass
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        x_dev.copy_(x_host, non_blocking=True)
-        logits_host = step(x_dev).float().cpu()
+    n_out = 0
+    for logits_host in pipe.stream(x_hosts[i & 1] for i in range(args.steps)):
+        n_out += logits_host.shape[0]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert n_out == B * args.steps
+    x_host = x_hosts[0]
 
     t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -262,10 +267,11 @@ def run_ours(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{args.dtype},{B}")
     roof = None
-    key = next((k for k in kstats if k.startswith("ss2d_core_fwd") and "L=3136" in k), None)
+    L1 = (RES // 4) ** 2
+    key = next((k for k in kstats if k.startswith("ss2d_core_fwd") and f"L={L1}," in k), None)
     if key:
         st = kstats[key]
-        D, R, N, K, L = 96, 3, 16, 4, 3136
+        D, R, N, K, L = 96, 3, 16, 4, L1
         es_x = 2 if args.dtype == "bf16" else 4           # xc element size; proj and ydir are fp32
         alg_bytes = B * L * (D * es_x + D * 4 + 4 * K * (R + 2 * N))
         exps = B * K * D * L * N
@@ -273,6 +279,8 @@ def run_ours(args):
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "kernel": key, "avg_ms": round(st["avg_ms"], 4), "launches": st["count"],
                 "peak_source": peak_src,
+                # what the reference-layout operator would have to move for the same work (interface level)
+                "interface_equivalent_gbs": round(4 * B * L * (3 * K * D + 2 * K * N) / (st["avg_ms"] * 1e-3) / 1e9, 1),
                 "alu": {"bound": "mufu_ex2", "achieved_gexp_s": round(exps / (st["avg_ms"] * 1e-3) / 1e9, 1),
                         "peak_gexp_s": round(MUFU_EXP_PER_S / 1e9, 1),
                         "frac": round(exps / (st["avg_ms"] * 1e-3) / MUFU_EXP_PER_S, 4)}}
@@ -286,7 +294,8 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"batch-sharded replicas x{world}",
-                   "l2": "inputs (154 MB at batch 256) and activations exceed the 126 MB L2; no flush needed"},
+                   "l2": f"inputs ({B * 3 * RES * RES * 4 / 1e6:.0f} MB per step) and activations exceed the 126 MB L2; no flush needed",
+                   "batch_sweep": "profiles/README.md (256 / 512 / 1024 per GPU)"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                 "d2h_bytes_per_step": B * NUM_CLASSES * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -362,11 +371,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step (BASELINE configs[2]: 256-1024)")
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--res", type=int, default=224, help="image side; 512 with --batch 32 is BASELINE configs[4]")
     args = ap.parse_args()
+    global RES
+    RES = args.res
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":

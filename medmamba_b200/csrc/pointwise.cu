@@ -89,6 +89,99 @@ dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 in / bf16 out build of the same convolution (the autocast layout): a thread owns 8 channels -- one 128-bit
+// load per neighbour instead of a 64-bit one -- and a strip of WS output pixels; weights come from shared memory
+// one row of taps at a time (72 of them would not fit in registers beside the 8 x WS accumulators).
+template <int WS>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int D,
+                             int64_t x_pix, int64_t x_batch) {
+    extern __shared__ __align__(16) float swt[];        // [tap][D]
+    for (int i = threadIdx.x; i < D * 9; i += blockDim.x) swt[(i % 9) * D + i / 9] = __ldg(wgt + i);
+    __syncthreads();
+    const int C8 = D / 8;
+    const int strips = (W + WS - 1) / WS;
+    const uint32_t total = (uint32_t)B * H * strips * C8;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % (uint32_t)C8);
+        uint32_t r = idx / (uint32_t)C8;
+        const int st = (int)(r % (uint32_t)strips); r /= (uint32_t)strips;
+        const int h = (int)(r % (uint32_t)H);
+        const int b = (int)(r / (uint32_t)H);
+        const int c = c8 * 8, w0 = st * WS;
+        float acc[WS][8];
+        {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (bias) { b0 = __ldg(reinterpret_cast<const float4*>(bias + c)); b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4)); }
+#pragma unroll
+            for (int i = 0; i < WS; ++i) {
+                acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+                acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
+            }
+        }
+        const __nv_bfloat16* xb = x + (int64_t)b * x_batch + c;
+        // all 3 x (WS + 2) neighbour loads issued up front from clamped coordinates, masked afterwards
+        uint4 nb[3][WS + 2];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int hy = min(max(h + dy - 1, 0), H - 1);
+#pragma unroll
+            for (int j = 0; j < WS + 2; ++j) {
+                const int wx = min(max(w0 + j - 1, 0), W - 1);
+                nb[dy][j] = __ldg(reinterpret_cast<const uint4*>(xb + ((int64_t)hy * W + wx) * x_pix));
+            }
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const bool hok = (h + dy - 1 >= 0) && (h + dy - 1 < H);
+            float wk[3][8];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 w0v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c);
+                const float4 w1v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c + 4);
+                wk[dx][0] = w0v.x; wk[dx][1] = w0v.y; wk[dx][2] = w0v.z; wk[dx][3] = w0v.w;
+                wk[dx][4] = w1v.x; wk[dx][5] = w1v.y; wk[dx][6] = w1v.z; wk[dx][7] = w1v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < WS + 2; ++j) {
+                const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
+                const uint32_t wds[4] = {nb[dy][j].x, nb[dy][j].y, nb[dy][j].z, nb[dy][j].w};
+                float vv[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // bf16 -> fp32 is a shift: low half is element 2e, high half element 2e + 1
+                    vv[2 * e] = ok ? __uint_as_float(wds[e] << 16) : 0.f;
+                    vv[2 * e + 1] = ok ? __uint_as_float(wds[e] & 0xffff0000u) : 0.f;
+                }
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int i = j - dx;
+                    if (i >= 0 && i < WS) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wk[dx][e], vv[e], acc[i][e]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < WS; ++i) {
+            const int wx = w0 + i;
+            if (wx < W) {
+                uint4 o;
+                uint32_t* ow = &o.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 pr = __floats2bfloat162_rn(silu_f(acc[i][2 * e]), silu_f(acc[i][2 * e + 1]));
+                    ow[e] = *reinterpret_cast<const uint32_t*>(&pr);
+                }
+                *reinterpret_cast<uint4*>(out + (((int64_t)b * H + h) * W + wx) * D + c) = o;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One warp per token: y = ((y0 + y2) + y1) + y3 over the four direction slices of ydir (B, L, 4, D)
 // -- the order of `y1 + y2 + y3 + y4` at MedMamba.py:298, whose operands are out0, flipped out2,
 // transposed out1, flipped-transposed out3 (MedMamba.py:286) -- then LayerNorm over D and * SiLU(z).
@@ -154,41 +247,46 @@ outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, c
 // Plain LayerNorm over the channels of a channels-last token matrix (warp per token).  Used for ln_1 on the
 // strided right half of the residual stream (MedMamba.py:351), the patch-embed norm (:75) and the patch-merging
 // norm (:116): rows of 48..1536 channels, for which a block-per-row LayerNorm leaves most threads idle.
-template <int V, typename in_t, typename out_t>
+// G lanes per token (32, or 16 / 8 for narrow rows so that few lanes idle: ln_1 of stage 1 has 12 float4 per token).
+template <int V, typename in_t, typename out_t, int G = 32>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      out_t* __restrict__ out, int64_t tokens, int D, int64_t x_pix, float eps) {
-    const int lane = threadIdx.x & 31;
+    constexpr int TPW = 32 / G;                      // tokens per warp
+    const int lane = threadIdx.x & 31, gl = lane % G;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int C4 = D / 4;
-    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+    const int64_t ngroups = (tokens + TPW - 1) / TPW;
+    for (int64_t grp = warp; grp < ngroups; grp += nwarps) {
+        const int64_t tok = grp * TPW + lane / G;
+        const bool tvalid = tok < tokens;
         float4 v[V];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            v[i] = c4 < C4 ? load4<in_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c4 = gl + G * i;
+            v[i] = (tvalid && c4 < C4) ? load4<in_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        for (int off = G / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         const float mean = sum / (float)D;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (lane + 32 * i < C4) {
+            if (gl + G * i < C4) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
                 sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        for (int off = G / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
         const float rstd = rsqrtf(sq / (float)D + eps);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            if (c4 < C4) {
+            const int c4 = gl + G * i;
+            if (tvalid && c4 < C4) {
                 const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
                 const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
                 float4 o;
@@ -279,6 +377,15 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
             reinterpret_cast<OUT*>(out), batch, H, W, D, x_pixel_stride, x_batch_stride);                        \
         return launch_status();                                                                                  \
     } while (0)
+    if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16 && D % 8 == 0 && x_pixel_stride % 8 == 0 && x_batch_stride % 8 == 0 &&
+        reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+        (!bias || reinterpret_cast<uintptr_t>(bias) % 16 == 0)) {
+        const int64_t items8 = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 8);
+        dwconv3x3_silu_bf16x8_kernel<WS><<<grid_for(items8, 256), 256, (size_t)D * 36, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), weight, bias, reinterpret_cast<__nv_bfloat16*>(out), batch, H, W, D,
+            x_pixel_stride, x_batch_stride);
+        return launch_status();
+    }
     if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_DW(float, float);
     if (in_dtype == MMB_BF16 && out_dtype == MMB_F32) MMB_DW(__nv_bfloat16, float);
     if (in_dtype == MMB_F16 && out_dtype == MMB_F32) MMB_DW(__half, float);
@@ -358,21 +465,23 @@ extern "C" int mmb_layernorm_fwd(const void* x, const float* gamma, const float*
     if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     if (tokens == 0) return MMB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int grid = grid_for(tokens * 32, 256);
-#define MMB_LN(V, TI, TO)                                                                                        \
+    #define MMB_LN(V, TI, TO, G)                                                                                     \
     do {                                                                                                         \
         if (!aligned_for4<TI>(x) || !aligned_for4<TO>(out)) return MMB_ERR_UNSUPPORTED;                          \
-        layernorm_fwd_kernel<V, TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(x), gamma, beta,       \
-            reinterpret_cast<TO*>(out), tokens, D, x_pixel_stride, eps);                                         \
+        layernorm_fwd_kernel<V, TI, TO, G><<<grid_for(tokens * G, 256), 256, 0, st>>>(                           \
+            reinterpret_cast<const TI*>(x), gamma, beta, reinterpret_cast<TO*>(out), tokens, D, x_pixel_stride,  \
+            eps);                                                                                                \
         return launch_status();                                                                                  \
     } while (0)
 #define MMB_LN_V(TI, TO)                                                                                         \
     do {                                                                                                         \
-        if (D <= 128) MMB_LN(1, TI, TO);                                                                         \
-        if (D <= 256) MMB_LN(2, TI, TO);                                                                         \
-        if (D <= 512) MMB_LN(4, TI, TO);                                                                         \
-        if (D <= 1024) MMB_LN(8, TI, TO);                                                                        \
-        MMB_LN(16, TI, TO);                                                                                      \
+        if (D <= 32) MMB_LN(1, TI, TO, 8);                                                                       \
+        if (D <= 64) MMB_LN(1, TI, TO, 16);                                                                      \
+        if (D <= 128) MMB_LN(1, TI, TO, 32);                                                                         \
+        if (D <= 256) MMB_LN(2, TI, TO, 32);                                                                         \
+        if (D <= 512) MMB_LN(4, TI, TO, 32);                                                                         \
+        if (D <= 1024) MMB_LN(8, TI, TO, 32);                                                                        \
+        MMB_LN(16, TI, TO, 32);                                                                                    \
     } while (0)
     if (in_dtype == MMB_F32 && out_dtype == MMB_F32) MMB_LN_V(float, float);
     if (in_dtype == MMB_F32 && out_dtype == MMB_BF16) MMB_LN_V(float, __nv_bfloat16);

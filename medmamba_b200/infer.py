@@ -1,0 +1,79 @@
+"""Host-facing inference call: pinned host images in, host logits out, with the host->device copy of the next
+batch overlapped with the forward pass of the current one.
+
+The reference's consumers (test.py:60-75, app_streamlit_demo.py:95-110) call ``net(img.to(device))`` and read
+the logits back batch by batch; ``InferencePipeline`` is that loop with two device input buffers, a copy
+stream and pinned logits buffers, so that PCIe traffic and the forward pass run concurrently.  Outputs are the
+same tensors ``net`` would produce (tests/test_infer_gpu.py).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, Optional
+
+import torch
+
+
+class InferencePipeline:
+    def __init__(self, net: torch.nn.Module, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, device=None):
+        self.net = net.eval()
+        self.device = torch.device(device) if device is not None else next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("InferencePipeline runs on CUDA only (there is no CPU path)")
+        self.autocast_dtype = autocast_dtype
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._in = [None, None]          # device input buffers
+        self._out = [None, None]         # pinned host logits
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of slot s finished
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]   # forward that read slot s finished
+        self._done = [torch.cuda.Event(), torch.cuda.Event()]       # D2H of slot s finished
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            if self.autocast_dtype is None:
+                return self.net(x)
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                return self.net(x)
+
+    def _stage(self, slot: int, host: torch.Tensor) -> None:
+        buf = self._in[slot]
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = self._in[slot] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._consumed[slot])        # the previous forward on this buffer is over
+            buf.copy_(host, non_blocking=True)
+            self._ready[slot].record(self.copy_stream)
+
+    def __call__(self, host_images: torch.Tensor) -> torch.Tensor:
+        """One batch, synchronously: (B, 3, H, W) host tensor -> (B, num_classes) fp32 host logits."""
+        return next(self.stream([host_images]))
+
+    def stream(self, batches: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
+        """Yields fp32 host logits per batch, in order.  While batch i is in the forward pass, batch i+1 is on
+        its way over PCIe and the logits of batch i-1 are being read back."""
+        main = torch.cuda.current_stream(self.device)
+        it = iter(batches)
+        pending = None                 # (slot, logits shape) whose D2H is in flight
+        cur = next(it, None)
+        if cur is None:
+            return
+        slot = 0
+        self._stage(slot, cur)
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self._stage(slot ^ 1, nxt)
+            main.wait_event(self._ready[slot])
+            logits = self._forward(self._in[slot]).float()
+            self._consumed[slot].record(main)
+            out = self._out[slot]
+            if out is None or out.shape != logits.shape:
+                out = self._out[slot] = torch.empty(logits.shape, dtype=torch.float32).pin_memory()
+            out.copy_(logits, non_blocking=True)
+            self._done[slot].record(main)
+            if pending is not None:
+                self._done[pending].synchronize()
+                yield self._out[pending].clone()
+            pending = slot
+            cur, slot = nxt, slot ^ 1
+        self._done[pending].synchronize()
+        yield self._out[pending].clone()

@@ -46,6 +46,22 @@ def test_dwconv_silu(B, H, W, D):
     assert_close(got.permute(0, 3, 1, 2), want, 1e-5, 1e-6, "dwconv+silu no bias")
 
 
+@pytest.mark.parametrize("B,H,W,D", [(1, 1, 1, 8), (2, 5, 7, 16), (3, 9, 8, 96), (2, 14, 14, 384), (1, 7, 3, 40), (2, 56, 56, 96),
+                                      (1, 6, 6, 12)])
+def test_dwconv_silu_bf16(B, H, W, D):
+    """bf16 in / bf16 out (autocast layout; 8 channels per thread when D % 8 == 0): exact fp64 conv of the bf16
+    inputs, rounded once to bf16 at the end."""
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(D + W)
+    xz = torch.randn(B, H, W, 2 * D, generator=g).bfloat16()
+    w = torch.randn(D, 1, 3, 3, generator=g) * 0.5
+    bias = torch.randn(D, generator=g)
+    want = F.silu(F.conv2d(xz[..., :D].permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1, groups=D))
+    got = ops.dwconv3x3_silu(xz.cuda()[..., :D], w.cuda(), bias.cuda(), out_dtype=torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and got.shape == (B, H, W, D)
+    assert_close(got.permute(0, 3, 1, 2).float(), want, 2 ** -8, 1e-6, "dwconv+silu bf16")
+
+
 @pytest.mark.parametrize("B,H,W,c", [(1, 1, 1, 4), (2, 5, 7, 8), (2, 14, 14, 192), (3, 9, 4, 20)])
 def test_shuffle_cat_residual_bit_exact(B, H, W, c):
     from medmamba_b200 import ops
@@ -163,6 +179,55 @@ def test_vssm_t_config1_logits_and_top1():
     assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
 
 
+def test_core_long_sequence_config5_stage1():
+    """BASELINE config 5 (512x512 images): the stage-1 grid is 128x128, L = 16384 -- 512 ring blocks per row
+    direction, one column block per 4 columns -- against the fp64 oracle, model-like magnitudes."""
+    from medmamba_b200 import ops
+    B, H, W, D, R, N = 1, 128, 128, 96, 3, 16
+    prm = _random_ss2d_params(D, R, N, seed=5, stress=False)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, D, H, W, generator=g) * 0.1
+    ys = medmamba_ref.ss2d_core(x, prm["x_proj_weight"], prm["dt_projs_weight"], prm["dt_projs_bias"],
+                                prm["A_logs"], prm["Ds"], scan_fn=cscan_fn)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.pack_x_proj(prm["x_proj_weight"].cuda(), N, R)
+    proj = (xc.view(-1, D) @ wp.t()).view(B, H, W, 4, -1)
+    ydir = ops.ss2d_core(xc, proj, prm["dt_projs_weight"].cuda().contiguous(), prm["dt_projs_bias"].cuda().contiguous(),
+                         (-torch.exp(prm["A_logs"])).cuda().contiguous(), prm["Ds"].cuda().contiguous(), N, R)
+    for k, ref_i in enumerate([0, 2, 1, 3]):
+        want = ys[ref_i].reshape(B, D, H, W).permute(0, 2, 3, 1)
+        assert_close(ydir[..., k, :].cpu(), want, 1e-4, 1e-5, f"L=16384 direction {k}")
+        uD = (x * prm["Ds"].view(4, D)[k].view(1, D, 1, 1)).permute(0, 2, 3, 1)
+        assert_close(ydir[..., k, :].cpu() - uD, want - uD, 1e-4, 1e-5, f"L=16384 direction {k} minus u*D")
+
+
+def test_vssm_t_config5_fused_vs_reference_order():
+    """BASELINE config 5 end to end (MedMamba-T, 512x512, fp32): the fused path against the reference's op order
+    through selective_scan_fn (materialised cross-scan, mmb_scan_fwd at L = 16384, torch merge / LayerNorm) on
+    the same weights: logits allclose and identical top-1."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.medmamba_t(num_classes=6).cuda().eval()
+    x = torch.randn(2, 3, 512, 512, generator=torch.Generator().manual_seed(1)).cuda()
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = net(x)
+            for m in net.modules():
+                if isinstance(m, (mm.SS2D, mm.PatchEmbed2D, mm.PatchMerging2D)):
+                    m.fused = False
+                if isinstance(m, mm.SS_Conv_SSM):
+                    m.fast_cnn = False
+            ref_order = net(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert torch.isfinite(fused).all()
+    print("config-5 max |dlogit| fused vs reference order", (fused - ref_order).abs().max().item())
+    assert_close(fused, ref_order.double(), 1e-3, 1e-4, "config-5 logits")
+    assert torch.equal(fused.argmax(1), ref_order.argmax(1))
+
+
 def test_shuffle_mixed_dtype_autocast():
     """bf16 branches onto the fp32 residual stream (what autocast produces)."""
     from medmamba_b200 import ops
@@ -208,6 +273,7 @@ def test_vssm_t_bf16_top1_matches():
 
 
 @pytest.mark.parametrize("B,H,W,C,strided", [(2, 5, 7, 48, True), (1, 3, 3, 96, False), (2, 14, 14, 384, True),
+                                             (3, 5, 5, 16, True), (1, 7, 9, 32, False), (2, 3, 11, 64, True), (1, 1, 1, 4, False),
                                                (1, 4, 4, 1536, False), (3, 2, 9, 8, True)])
 def test_layernorm_kernel(B, H, W, C, strided):
     from medmamba_b200 import ops
