@@ -65,6 +65,24 @@ __device__ __forceinline__ float softplus_f(float x) {
     return x > 20.0f ? x : r;
 }
 
+// Two softplus evaluations with the series and the fix-up arithmetic issued as packed pairs.
+__device__ __forceinline__ void softplus2_f(float& r0, float& r1, float x0, float x1) {
+    const float v0 = ex2_approx(x0 * kLog2e), v1 = ex2_approx(x1 * kLog2e);
+    const float big0 = lg2_approx(1.0f + v0) * kLn2, big1 = lg2_approx(1.0f + v1) * kLn2;
+    float s0, s1;
+    fma2(s0, s1, v0, v1, -0.125f, -0.125f, 1.0f / 7.0f, 1.0f / 7.0f);
+    fma2(s0, s1, v0, v1, s0, s1, -1.0f / 6.0f, -1.0f / 6.0f);
+    fma2(s0, s1, v0, v1, s0, s1, 0.2f, 0.2f);
+    fma2(s0, s1, v0, v1, s0, s1, -0.25f, -0.25f);
+    fma2(s0, s1, v0, v1, s0, s1, 1.0f / 3.0f, 1.0f / 3.0f);
+    fma2(s0, s1, v0, v1, s0, s1, -0.5f, -0.5f);
+    fma2(s0, s1, v0, v1, s0, s1, 1.0f, 1.0f);
+    mul2(s0, s1, v0, v1, s0, s1);
+    const float q0 = v0 < 0.125f ? s0 : big0, q1 = v1 < 0.125f ? s1 : big1;
+    r0 = x0 > 20.0f ? x0 : q0;
+    r1 = x1 > 20.0f ? x1 : q1;
+}
+
 // d softplus / dx = sigmoid(x) (1 above the threshold, as torch's backward does).
 __device__ __forceinline__ float sigmoid_f(float x) {
     return rcp_approx(1.0f + ex2_approx(-x * kLog2e));

@@ -31,6 +31,7 @@
 namespace mmb {
 
 constexpr int kCoreStages = 4;
+constexpr bool kPackSoftplus = true;    // A/B on B200: packed pairs 0.9% faster over the four stage shapes
 constexpr int kCoreStageBytes = 16 * 1024;
 
 struct CoreFwdParams {
@@ -153,32 +154,49 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         if (p.dbg & 1) { while (!mbar_try_wait(&full[s], ph)) {} } else mbar_wait(&full[s], ph);
 
         const bool single_col = nwbox == 1;     // slot / position are then affine in the step index: no shuffles
-        // One group = four consecutive steps.  FULL groups carry no per-step validity predicates.
-        auto group = [&](auto full_tag, const int g0) {
-            constexpr bool FULL = decltype(full_tag)::value;
+        // One group = four consecutive steps.  MODE 0: ragged last group of a block (per-step validity predicates);
+        // MODE 3: full group, run-time direction, lane-table shuffles when the block spans several columns;
+        // MODE 1 / 2: full group of a single-column block walked forwards / backwards: slots and positions are
+        // base + i * constant, no predicates, no selects on the direction.
+        auto group = [&](auto mode_tag, const int g0) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            constexpr bool FULL = MODE != 0;
             int slot[4], pos[4];
             bool ok[4];
+            if (MODE == 0 || MODE == 3) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int tl = g0 + i;
-                ok[i] = FULL || tl < nsteps;
-                const int ti = ok[i] ? (rev ? nsteps - 1 - tl : tl) : 0;
-                if (single_col) { slot[i] = ti; pos[i] = pbase + ti * psh; }
-                else { slot[i] = __shfl_sync(0xffffffffu, slot_l, ti); pos[i] = __shfl_sync(0xffffffffu, pos_l, ti); }
+                for (int i = 0; i < 4; ++i) {
+                    const int tl = g0 + i;
+                    ok[i] = FULL || tl < nsteps;
+                    const int ti = ok[i] ? (rev ? nsteps - 1 - tl : tl) : 0;
+                    if (single_col) { slot[i] = ti; pos[i] = pbase + ti * psh; }
+                    else { slot[i] = __shfl_sync(0xffffffffu, slot_l, ti); pos[i] = __shfl_sync(0xffffffffu, pos_l, ti); }
+                }
+            } else {
+                const int t0 = MODE == 1 ? g0 : nsteps - 1 - g0;
+                const int p0 = pbase + t0 * psh;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ok[i] = true;
+                    slot[i] = MODE == 1 ? t0 + i : t0 - i;
+                    pos[i] = MODE == 1 ? p0 + i * psh : p0 - i * psh;
+                }
             }
             float uu[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) uu[i] = ok[i] ? to_f<xc_t>(xs[slot[i] * p.CT]) : 0.f;
             // delta = softplus(Wdt . dt_r + bias): each lane evaluates OWN of the four steps
             float down[OWN];
+            float raw[OWN];
+            bool okd[OWN];
 #pragma unroll
             for (int m = 0; m < OWN; ++m) {
-                int sl; bool okk;
-                if (S == 1) { sl = slot[m]; okk = ok[m]; }
+                int sl;
+                if (S == 1) { sl = slot[m]; okd[m] = ok[m]; }
                 else {
                     const int tl = g0 + q + S * m;
-                    okk = FULL || tl < nsteps;
-                    const int ti = okk ? (rev ? nsteps - 1 - tl : tl) : 0;
+                    okd[m] = FULL || tl < nsteps;
+                    const int ti = okd[m] ? (rev ? nsteps - 1 - tl : tl) : 0;
                     sl = single_col ? ti : __shfl_sync(0xffffffffu, slot_l, ti);
                 }
                 const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
@@ -189,8 +207,18 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                     fma2(acc0, acc1, Wd[4 * r4 + 0], Wd[4 * r4 + 1], v.x, v.y, acc0, acc1);
                     fma2(acc0, acc1, Wd[4 * r4 + 2], Wd[4 * r4 + 3], v.z, v.w, acc0, acc1);
                 }
-                const float sp = softplus_f(acc0 + acc1);
-                down[m] = okk ? sp : 0.f;
+                raw[m] = acc0 + acc1;
+            }
+            if (OWN % 2 == 0 && kPackSoftplus) {
+#pragma unroll
+                for (int m = 0; m < OWN; m += 2) softplus2_f(down[m], down[m + 1], raw[m], raw[m + 1]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < OWN; ++m) down[m] = softplus_f(raw[m]);
+            }
+            if (!FULL) {
+#pragma unroll
+                for (int m = 0; m < OWN; ++m) down[m] = okd[m] ? down[m] : 0.f;
             }
             float dl[4], du[4], y[4];
 #pragma unroll
@@ -240,8 +268,10 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
         };
         const int nfull = nsteps & ~3;
-        for (int g0 = 0; g0 < nfull; g0 += 4) group(std::true_type{}, g0);
-        if (nfull < nsteps) group(std::false_type{}, nfull);
+        if (!single_col || S != 1) { for (int g0 = 0; g0 < nfull; g0 += 4) group(std::integral_constant<int, 3>{}, g0); }
+        else if (!rev) { for (int g0 = 0; g0 < nfull; g0 += 4) group(std::integral_constant<int, 1>{}, g0); }
+        else { for (int g0 = 0; g0 < nfull; g0 += 4) group(std::integral_constant<int, 2>{}, g0); }
+        if (nfull < nsteps) group(std::integral_constant<int, 0>{}, nfull);
         if (p.hsave && cvalid) {
             float* hs = p.hsave + ((((int64_t)b * 4 + k) * p.NBmax + jb) * p.D + c) * kMaxState + 4 * q;
 #pragma unroll
