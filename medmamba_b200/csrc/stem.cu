@@ -9,28 +9,32 @@
 namespace mmb {
 
 // ------------------------------------------------------------------------------------------------
-// Patch embedding.  A CTA of 8 warps owns one output row (b, i): the 3 x 4 input rows it needs (12 x Win
-// floats) are staged in shared memory with coalesced 128-bit loads; the weights (E x 48, row pitch 52 floats:
-// conflict-free LDS.128 of 4 consecutive taps) are staged once per CTA, CTAs are persistent over the rows.
-// A warp takes groups of TT = 7 tokens; lane l owns output channels l, l+32, .. (M = E/32 of them) of all 7:
-// per 4 taps M weight LDS.128 + 7 broadcast input LDS.128 feed 28 M FMAs.  LayerNorm of a token is a warp
-// reduction over the lanes' M channels (two-pass, like layernorm_fwd_kernel).
+// Patch embedding.  A CTA of 4 warps owns 56 tokens of one output row (b, i): the 3 x 4 input row pieces it
+// needs are staged in shared memory with coalesced 128-bit loads; the weights (E x 48, row pitch 52 floats:
+// conflict-free LDS.128 of 4 consecutive taps) are staged once per CTA, CTAs are persistent over the units.
+// A warp takes TT = 14 tokens; lane l owns output channels l, l+32, .. (M = E/32 of them) of all 14: per 4 taps
+// M weight LDS.128 (4 shared-memory wavefronts each) + 14 broadcast input LDS.128 feed 56 M FMAs, which keeps
+// the FMA pipe, not shared memory, the busier one (7 tokens per warp: 1.43 ms, 14: see profiles/README.md).
+// LayerNorm of a token is a warp reduction over the lanes' M channels (two-pass, like layernorm_fwd_kernel).
 constexpr int kPeTaps = 48;      // 3 channels x 4 x 4
 constexpr int kPePitch = 52;
-constexpr int kPeTT = 7;
+constexpr int kPeTT = 14;
+constexpr int kPeWarps = 4;
+constexpr int kPeThreads = 32 * kPeWarps;
+constexpr int kPeChunk = kPeWarps * kPeTT;   // tokens per work unit: one group of kPeTT per warp
 
 template <int M, typename in_t>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kPeThreads, 4)
 patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ cbias,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                       int B, int Hin, int Win, float eps) {
     constexpr int E = 32 * M;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;                       // [E][kPePitch]
-    float* sx = smem + E * kPePitch;        // [12][Win]
+    float* sx = smem + E * kPePitch;        // [12][kPeChunk] float4
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ho = Hin / 4, Wo = Win / 4;
-    for (int i = tid; i < E * kPeTaps; i += blockDim.x) sw[(i / kPeTaps) * kPePitch + i % kPeTaps] = __ldg(wgt + i);
+    for (int i = tid; i < E * kPeTaps; i += kPeThreads) sw[(i / kPeTaps) * kPePitch + i % kPeTaps] = __ldg(wgt + i);
     float cb[M], gm[M], bt[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
@@ -39,42 +43,73 @@ patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
         gm[m] = __ldg(gamma + oc);
         bt[m] = __ldg(beta + oc);
     }
-    const int W4 = Win / 4;
-    const int groups = (Wo + kPeTT - 1) / kPeTT;
-    for (int row = blockIdx.x; row < B * Ho; row += gridDim.x) {
+    // Work unit: (image b, output row i, chunk of kPeChunk = 56 tokens = 224 input columns): 4 warps x 14 tokens.
+    // The strip of the next unit travels global -> registers while this one is computed, registers -> shared
+    // memory afterwards, so the DRAM latency hides behind the FMAs (a strip is 12 x 56 float4: 6 per thread).
+    constexpr int kPeStage = (12 * kPeChunk + kPeThreads - 1) / kPeThreads;
+    const int nchunks = (Wo + kPeChunk - 1) / kPeChunk;
+    const int nunits = B * Ho * nchunks;
+    float4 nxt[kPeStage];
+    auto fetch = [&](int unit) {
+        const int ch = unit % nchunks, row = unit / nchunks;
         const int b = row / Ho, i = row - b * Ho;
-        __syncthreads();                     // previous row fully consumed (and the weights staged)
-        for (int idx = tid; idx < 12 * W4; idx += blockDim.x) {
-            const int rr = idx / W4, w4 = idx - rr * W4;      // rr = c * 4 + r
-            const int c = rr >> 2, r = rr & 3;
-            const in_t* src = x + (((int64_t)b * 3 + c) * Hin + 4 * i + r) * Win + 4 * w4;
-            *reinterpret_cast<float4*>(sx + rr * Win + 4 * w4) = load4<in_t>(src);
+        const int w4n = min(kPeChunk, Wo - ch * kPeChunk);          // float4 (= tokens) per strip row
+#pragma unroll
+        for (int u = 0; u < kPeStage; ++u) {
+            const int idx = tid + u * kPeThreads;
+            const int rr = idx / kPeChunk, w4 = idx - rr * kPeChunk;      // rr = c * 4 + r
+            if (rr < 12 && w4 < w4n) {
+                const in_t* src = x + (((int64_t)b * 3 + (rr >> 2)) * Hin + 4 * i + (rr & 3)) * Win + 4 * (ch * kPeChunk + w4);
+                nxt[u] = load4<in_t>(src);
+            } else {
+                nxt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
+    };
+    auto park = [&]() {
+#pragma unroll
+        for (int u = 0; u < kPeStage; ++u) {
+            const int idx = tid + u * kPeThreads;
+            const int rr = idx / kPeChunk, w4 = idx - rr * kPeChunk;
+            if (rr < 12) *reinterpret_cast<float4*>(sx + (rr * kPeChunk + w4) * 4) = nxt[u];
+        }
+    };
+    if ((int)blockIdx.x < nunits) fetch(blockIdx.x);
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int ch = unit % nchunks, row = unit / nchunks;
+        const int b = row / Ho, i = row - b * Ho;
+        const int ntok = min(kPeChunk, Wo - ch * kPeChunk);
+        __syncthreads();                     // previous unit fully consumed (and the weights staged)
+        park();
         __syncthreads();
-        for (int g = warp; g < groups; g += 8) {
-            const int t0 = g * kPeTT;
+        if (unit + (int)gridDim.x < nunits) fetch(unit + gridDim.x);
+        const int t0 = warp * kPeTT;         // first token of this warp inside the chunk
+        if (t0 < ntok) {
             float acc[kPeTT][M];
 #pragma unroll
             for (int t = 0; t < kPeTT; ++t)
 #pragma unroll
                 for (int m = 0; m < M; ++m) acc[t][m] = cb[m];
-#pragma unroll 2
+#pragma unroll 1
             for (int rr = 0; rr < 12; ++rr) {
                 float4 wv[M];
 #pragma unroll
                 for (int m = 0; m < M; ++m)
                     wv[m] = *reinterpret_cast<const float4*>(sw + (lane + 32 * m) * kPePitch + 4 * rr);
+                // tokens past the end of a ragged chunk read stale strip data; their results are never stored.
+                // Two tokens at a time, tap-major: 2 M independent FMAs between dependent ones.
 #pragma unroll
-                for (int t = 0; t < kPeTT; ++t) {
-                    const int tt = min(t0 + t, Wo - 1);
-                    const float4 xv = *reinterpret_cast<const float4*>(sx + rr * Win + 4 * tt);
+                for (int t = 0; t < kPeTT; t += 2) {
+                    const float4 xa = *reinterpret_cast<const float4*>(sx + (rr * kPeChunk + t0 + t) * 4);
+                    const float4 xb = *reinterpret_cast<const float4*>(sx + (rr * kPeChunk + t0 + t + 1) * 4);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        acc[t][m] = fmaf(wv[m].x, xv.x, acc[t][m]);
-                        acc[t][m] = fmaf(wv[m].y, xv.y, acc[t][m]);
-                        acc[t][m] = fmaf(wv[m].z, xv.z, acc[t][m]);
-                        acc[t][m] = fmaf(wv[m].w, xv.w, acc[t][m]);
-                    }
+                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].x, xa.x, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].x, xb.x, acc[t + 1][m]); }
+#pragma unroll
+                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].y, xa.y, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].y, xb.y, acc[t + 1][m]); }
+#pragma unroll
+                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].z, xa.z, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].z, xb.z, acc[t + 1][m]); }
+#pragma unroll
+                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].w, xa.w, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].w, xb.w, acc[t + 1][m]); }
                 }
             }
             float sum[kPeTT], sq[kPeTT];
@@ -101,9 +136,9 @@ patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
                 for (int t = 0; t < kPeTT; ++t) sq[t] += __shfl_xor_sync(0xffffffffu, sq[t], off);
 #pragma unroll
             for (int t = 0; t < kPeTT; ++t) {
-                if (t0 + t < Wo) {
+                if (t0 + t < ntok) {
                     const float rstd = rsqrtf(sq[t] / (float)E + eps);
-                    float* o = out + (((int64_t)b * Ho + i) * Wo + t0 + t) * E + lane;
+                    float* o = out + (((int64_t)b * Ho + i) * Wo + ch * kPeChunk + t0 + t) * E + lane;
 #pragma unroll
                     for (int m = 0; m < M; ++m) o[32 * m] = fmaf(acc[t][m] * rstd, gm[m], bt[m]);
                 }
@@ -185,11 +220,10 @@ extern "C" int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const 
     if (Hin % 4 != 0 || Win % 4 != 0 || embed_dim % 32 != 0 || embed_dim > 128) return MMB_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) % 4 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
-    const size_t smem = sizeof(float) * ((size_t)embed_dim * kPePitch + 12 * (size_t)Win);
-    if (smem > 200 * 1024) return MMB_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * ((size_t)embed_dim * kPePitch + 12 * 4 * (size_t)kPeChunk);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const long rows = (long)batch * (Hin / 4);
-    const int grid = (int)(rows < 2L * num_sms() ? rows : 2L * num_sms());
+    const long units = (long)batch * (Hin / 4) * ((Win / 4 + kPeChunk - 1) / kPeChunk);
+    const int grid = (int)(units < 4L * num_sms() ? units : 4L * num_sms());
 #define MMB_PE(M, TI)                                                                                             \
     do {                                                                                                          \
         if (!aligned4<TI>(x)) return MMB_ERR_UNSUPPORTED;                                                         \
@@ -198,7 +232,7 @@ extern "C" int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const 
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
             if (e != cudaSuccess) return cuda_status(e);                                                          \
         }                                                                                                         \
-        kern<<<grid, 256, smem, st>>>(reinterpret_cast<const TI*>(x), weight, conv_bias, gamma, beta, out, batch, \
+        kern<<<grid, kPeThreads, smem, st>>>(reinterpret_cast<const TI*>(x), weight, conv_bias, gamma, beta, out, batch, \
                                       Hin, Win, eps);                                                             \
         return launch_status();                                                                                   \
     } while (0)

@@ -16,10 +16,10 @@ for r in rows:
         recs.append((d["Kernel Name"], float(d["Metric Value"].replace(",", "")), d["Grid Size"], d["Block Size"]))
     except ValueError:
         pass
-# the last forward pass: from the last patch-embed convolution onwards (bench runs warm-up steps first)
+# the last forward pass: from the last patch-embed kernel onwards (bench runs warm-up steps first)
 names = [n for n, *_ in recs]
-starts = [i for i, n in enumerate(names) if "layernorm_fwd_kernel<1, float, float>" in n or "layernorm_fwd_kernel<1, __nv_bfloat16, float>" in n]
-lo = starts[-1] - 3 if starts else 0
+starts = [i for i, n in enumerate(names) if "patch_embed_ln_kernel" in n]
+lo = starts[-1] if starts else 0
 sel = recs[max(lo, 0):]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, v, g, b in sel:
