@@ -13,18 +13,20 @@ namespace mmb {
 // needs are staged in shared memory with coalesced 128-bit loads; the weights (E x 48, row pitch 52 floats:
 // conflict-free LDS.128 of 4 consecutive taps) are staged once per CTA, CTAs are persistent over the units.
 // A warp takes TT = 14 tokens; lane l owns output channels l, l+32, .. (M = E/32 of them) of all 14: per 4 taps
-// M weight LDS.128 (4 shared-memory wavefronts each) + 14 broadcast input LDS.128 feed 56 M FMAs, which keeps
-// the FMA pipe, not shared memory, the busier one (7 tokens per warp: 1.43 ms, 14: see profiles/README.md).
+// M weight LDS.128 + 14 broadcast input LDS.128 feed 56 M FMAs, issued as packed FFMA2 over token pairs (the
+// strip is stored pair-interleaved for that).  Measured at batch 1024: 1.43 ms for the first version, 1.01 ms
+// now; 8 tokens per warp at 28 warps per SM is no faster (1.06 ms) -- see profiles/README.md.
 // LayerNorm of a token is a warp reduction over the lanes' M channels (two-pass, like layernorm_fwd_kernel).
 constexpr int kPeTaps = 48;      // 3 channels x 4 x 4
 constexpr int kPePitch = 52;
 constexpr int kPeTT = 14;
 constexpr int kPeWarps = 4;
 constexpr int kPeThreads = 32 * kPeWarps;
+constexpr int kPeCtasPerSm = 4;
 constexpr int kPeChunk = kPeWarps * kPeTT;   // tokens per work unit: one group of kPeTT per warp
 
 template <int M, typename in_t>
-__global__ void __launch_bounds__(kPeThreads, 4)
+__global__ void __launch_bounds__(kPeThreads, kPeCtasPerSm)
 patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ cbias,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                       int B, int Hin, int Win, float eps) {
@@ -71,7 +73,11 @@ patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
         for (int u = 0; u < kPeStage; ++u) {
             const int idx = tid + u * kPeThreads;
             const int rr = idx / kPeChunk, w4 = idx - rr * kPeChunk;
-            if (rr < 12) *reinterpret_cast<float4*>(sx + (rr * kPeChunk + w4) * 4) = nxt[u];
+            if (rr < 12) {
+                // pair layout: tokens (2p, 2p+1) interleaved per tap, so one LDS.128 yields two packed FMA operands
+                float* d = sx + ((rr * (kPeChunk / 2) + (w4 >> 1)) * 4) * 2 + (w4 & 1);
+                d[0] = nxt[u].x; d[2] = nxt[u].y; d[4] = nxt[u].z; d[6] = nxt[u].w;
+            }
         }
     };
     if ((int)blockIdx.x < nunits) fetch(blockIdx.x);
@@ -97,19 +103,19 @@ patch_embed_ln_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
                 for (int m = 0; m < M; ++m)
                     wv[m] = *reinterpret_cast<const float4*>(sw + (lane + 32 * m) * kPePitch + 4 * rr);
                 // tokens past the end of a ragged chunk read stale strip data; their results are never stored.
-                // Two tokens at a time, tap-major: 2 M independent FMAs between dependent ones.
+                // Two tokens per packed FMA (FFMA2: the kernel is issue-bound with scalar FFMA), tap-major.
+                const float4* sp = reinterpret_cast<const float4*>(sx) + (rr * (kPeChunk / 2) + (t0 >> 1)) * 2;
 #pragma unroll
                 for (int t = 0; t < kPeTT; t += 2) {
-                    const float4 xa = *reinterpret_cast<const float4*>(sx + (rr * kPeChunk + t0 + t) * 4);
-                    const float4 xb = *reinterpret_cast<const float4*>(sx + (rr * kPeChunk + t0 + t + 1) * 4);
+                    const float4 q0 = sp[t], q1 = sp[t + 1];      // (a.x b.x a.y b.y), (a.z b.z a.w b.w)
 #pragma unroll
-                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].x, xa.x, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].x, xb.x, acc[t + 1][m]); }
+                    for (int m = 0; m < M; ++m) fma2(acc[t][m], acc[t + 1][m], wv[m].x, wv[m].x, q0.x, q0.y, acc[t][m], acc[t + 1][m]);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].y, xa.y, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].y, xb.y, acc[t + 1][m]); }
+                    for (int m = 0; m < M; ++m) fma2(acc[t][m], acc[t + 1][m], wv[m].y, wv[m].y, q0.z, q0.w, acc[t][m], acc[t + 1][m]);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].z, xa.z, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].z, xb.z, acc[t + 1][m]); }
+                    for (int m = 0; m < M; ++m) fma2(acc[t][m], acc[t + 1][m], wv[m].z, wv[m].z, q1.x, q1.y, acc[t][m], acc[t + 1][m]);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) { acc[t][m] = fmaf(wv[m].w, xa.w, acc[t][m]); acc[t + 1][m] = fmaf(wv[m].w, xb.w, acc[t + 1][m]); }
+                    for (int m = 0; m < M; ++m) fma2(acc[t][m], acc[t + 1][m], wv[m].w, wv[m].w, q1.z, q1.w, acc[t][m], acc[t + 1][m]);
                 }
             }
             float sum[kPeTT], sq[kPeTT];
@@ -223,7 +229,7 @@ extern "C" int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const 
     const size_t smem = sizeof(float) * ((size_t)embed_dim * kPePitch + 12 * 4 * (size_t)kPeChunk);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long units = (long)batch * (Hin / 4) * ((Win / 4 + kPeChunk - 1) / kPeChunk);
-    const int grid = (int)(units < 4L * num_sms() ? units : 4L * num_sms());
+    const int grid = (int)(units < (long)kPeCtasPerSm * num_sms() ? units : (long)kPeCtasPerSm * num_sms());
 #define MMB_PE(M, TI)                                                                                             \
     do {                                                                                                          \
         if (!aligned4<TI>(x)) return MMB_ERR_UNSUPPORTED;                                                         \

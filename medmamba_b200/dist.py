@@ -70,30 +70,32 @@ class GradAllReducer:
         if cur:
             self.buckets.append(cur)
         self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device) for b in self.buckets]
+        self.views: List[List[torch.Tensor]] = []          # per bucket: the slice of the flat buffer of every parameter
+        for b, flat in zip(self.buckets, self.flat):
+            off, vs = 0, []
+            for p in b:
+                vs.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self.views.append(vs)
 
     def reduce(self) -> None:
         if self.world == 1:
             return
         works = []
-        for bucket, flat in zip(self.buckets, self.flat):
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                if p.grad is None:
-                    flat[off:off + n].zero_()
-                else:
-                    flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
+        for bucket, flat, views in zip(self.buckets, self.flat, self.views):
+            missing = [v for p, v in zip(bucket, views) if p.grad is None]
+            if missing:
+                torch._foreach_zero_(missing)
+            have = [(v, p.grad) for p, v in zip(bucket, views) if p.grad is not None]
+            if have:
+                # one multi-tensor kernel per bucket instead of one copy per parameter (~300 parameters)
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
             works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
         inv = 1.0 / self.world
-        for bucket, flat, w in zip(self.buckets, self.flat, works):
+        for bucket, flat, views, w in zip(self.buckets, self.flat, self.views, works):
             w.wait()
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                g = flat[off:off + n].view_as(p) * inv
+            flat.mul_(inv)
+            for p, v in zip(bucket, views):
                 if p.grad is None:
-                    p.grad = g.to(p.dtype).clone()
-                else:
-                    p.grad.copy_(g)
-                off += n
+                    p.grad = v.to(p.dtype).clone()
+            torch._foreach_copy_([p.grad for p in bucket], views)
