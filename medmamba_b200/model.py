@@ -201,7 +201,8 @@ class SS2D(nn.Module):
         return self.out_proj(y.to(xz.dtype) if y.dtype != xz.dtype else y)
 
     def forward(self, x: torch.Tensor, **kwargs):
-        use_fused = self.fused and x.is_cuda and self.d_conv == 3 and ops.fused_available()
+        use_fused = (self.fused and x.is_cuda and self.d_conv == 3 and ops.fused_available()
+                     and not ops.has_hooks(self.conv2d, self.act, self.out_norm))
         out = self._forward_fused(x) if use_fused else self._forward_reference_order(x)
         return out if self.dropout is None else self.dropout(out)
 
@@ -277,7 +278,8 @@ class SS_Conv_SSM(nn.Module):
     def _cnn_fast_ok(self, left: torch.Tensor) -> bool:
         return (getattr(self, "fast_cnn", True) and left.is_cuda and not self.training and left.shape[-1] % 4 == 0
                 and left.dtype in (torch.float32, torch.bfloat16) and ops.fused_available()
-                and not ops.needs_autograd(left, *self.conv33conv33conv11.parameters()))
+                and not ops.needs_autograd(left, *self.conv33conv33conv11.parameters())
+                and not ops.has_hooks(self.conv33conv33conv11))
 
     def forward(self, input: torch.Tensor):
         left, right = input.chunk(2, dim=-1)

@@ -148,7 +148,7 @@ def fast_patch_embed_ok(x: torch.Tensor, proj, norm) -> bool:
             and tuple(proj.dilation) == (1, 1) and proj.groups == 1 and proj.out_channels % 32 == 0
             and proj.out_channels <= 128 and x.shape[1] == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
             and x.dtype in (torch.float32, torch.bfloat16)
-            and not needs_autograd(x, proj.weight, proj.bias, norm.weight, norm.bias))
+            and not needs_autograd(x, proj.weight, proj.bias, norm.weight, norm.bias) and not has_hooks(proj, norm))
 
 
 def patch_merge_ln(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torch.Tensor:
@@ -172,7 +172,7 @@ def fast_patch_merge_ok(x: torch.Tensor, ln) -> bool:
     return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine
             and ln.bias is not None and x.shape[-1] % 4 == 0 and x.shape[-1] <= 512
             and tuple(ln.normalized_shape) == (4 * x.shape[-1],) and x.dtype in (torch.float32, torch.bfloat16)
-            and not needs_autograd(x, ln.weight, ln.bias))
+            and not needs_autograd(x, ln.weight, ln.bias) and not has_hooks(ln))
 
 
 def affine_cast(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out_dtype) -> torch.Tensor:
@@ -188,12 +188,29 @@ def affine_cast(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out_d
     return out
 
 
+def has_hooks(*modules) -> bool:
+    """True if a forward / backward hook is registered on any of the modules or their submodules.  The fused
+    kernels use a module's parameters without calling it, so a hooked module (Grad-CAM hooks
+    ``conv33conv33conv11[-2]``, test.py:101 / grad_cam/utils.py:14-27) must take the module path."""
+    import torch.nn.modules.module as _m
+    if _m._global_forward_hooks or _m._global_forward_pre_hooks or _m._global_backward_hooks:
+        return True
+    for mod in modules:
+        if mod is None:
+            continue
+        for sub in mod.modules():
+            if (sub._forward_hooks or sub._forward_pre_hooks or sub._backward_hooks
+                    or getattr(sub, "_backward_pre_hooks", None)):
+                return True
+    return False
+
+
 def fast_layernorm_ok(x: torch.Tensor, ln) -> bool:
     """The hand-written LayerNorm applies: CUDA, no autograd, plain affine nn.LayerNorm over C % 4 == 0 <= 2048."""
     return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine
             and ln.bias is not None and len(ln.normalized_shape) == 1 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048
             and x.dtype in (torch.float32, torch.bfloat16)
-            and not needs_autograd(x, ln.weight, ln.bias))
+            and not needs_autograd(x, ln.weight, ln.bias) and not has_hooks(ln))
 
 
 def autocast_dtype(default):

@@ -29,3 +29,42 @@ def test_pipeline_rejects_cpu_module():
     import medmamba_b200 as mm
     with pytest.raises(RuntimeError):
         mm.InferencePipeline(mm.VSSM(depths=[1], dims=[32], num_classes=2))
+
+
+def test_gradcam_style_hooks_on_the_reference_target_layer():
+    """Grad-CAM consumer contract (test.py:101-108, grad_cam/utils.py:5-49): eval-mode model, forward and full
+    backward hooks on net.layers[-1].blocks[-1].conv33conv33conv11[-2], batch-1 backward from the top logit.
+    The hooked layer must be called (no fused bypass), activations / gradients must match the module path."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.VSSM(depths=[1, 1], dims=[32, 64], num_classes=3).cuda().eval()
+    target = net.layers[-1].blocks[-1].conv33conv33conv11[-2]
+    acts, grads = [], []
+    h1 = target.register_forward_hook(lambda m, i, o: acts.append(o.detach()))
+    h2 = target.register_full_backward_hook(lambda m, gi, go: grads.append(go[0].detach()))
+    x = torch.randn(1, 3, 64, 64, device="cuda")
+    try:
+        with torch.no_grad():
+            net(x)
+        assert len(acts) == 1, "a hooked layer must be called even under no_grad (fast path must step aside)"
+        acts.clear()
+        logits = net(x)
+        net.zero_grad()
+        logits[0, logits.argmax()].backward()
+        assert len(acts) == 1 and len(grads) == 1 and acts[0].shape == grads[0].shape
+        fused_act, fused_grad = acts[0].clone(), grads[0].clone()
+        for m in net.modules():                      # reference op order everywhere
+            if isinstance(m, (mm.SS2D, mm.PatchEmbed2D, mm.PatchMerging2D)):
+                m.fused = False
+        acts.clear(); grads.clear()
+        logits_ref = net(x)
+        net.zero_grad()
+        logits_ref[0, logits_ref.argmax()].backward()
+    finally:
+        h1.remove(); h2.remove()
+    assert torch.allclose(logits, logits_ref, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(fused_act, acts[0], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(fused_grad, grads[0], rtol=1e-2, atol=1e-5)
+    with torch.no_grad():                            # hooks removed: the fast path is back
+        y = net(x)
+    assert torch.allclose(y, logits.detach(), rtol=1e-3, atol=1e-4)

@@ -165,3 +165,32 @@ def test_seeded_init_equals_unmodified_reference():
 def test_flops_model_matches_survey_numbers():
     from medmamba_b200.flops import flops_selective_scan_ref
     assert flops_selective_scan_ref(B=64, L=3136, D=384, N=16) == pytest.approx(4.39e9, rel=0.01)
+
+
+def test_reference_checkpoint_format_round_trip(tmp_path):
+    """train.py:310-319 writes {'epoch', 'model_state_dict', 'optimizer_state_dict', 'best_acc', 'num_classes',
+    'class_indices', 'scheduler_state_dict'}; train.py:208-249 resumes from it.  The mirror's parameter order and
+    names are the reference's, so both the model and an AdamW / MultiStepLR state (indexed by parameter
+    position) written by one load into the other."""
+    import medmamba_b200 as mm
+    torch.manual_seed(1)
+    cfg = dict(depths=[1, 1], dims=[16, 32], num_classes=3)
+    src = mm.VSSM(**cfg)
+    opt = torch.optim.AdamW(src.parameters(), lr=1e-4, weight_decay=1e-4)            # train.py:190-192
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2, 4], gamma=0.1)
+    path = tmp_path / "ckpt.pth"
+    torch.save({"epoch": 3, "model_state_dict": src.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "best_acc": 0.5, "num_classes": 3, "class_indices": {"0": "a", "1": "b", "2": "c"},
+                "scheduler_state_dict": sched.state_dict()}, path)
+    ck = torch.load(path, map_location="cpu")
+    torch.manual_seed(2)
+    dst = mm.VSSM(**cfg)
+    dst.load_state_dict(ck["model_state_dict"])                                       # train.py:214
+    opt2 = torch.optim.AdamW(dst.parameters(), lr=1e-4, weight_decay=1e-4)
+    opt2.load_state_dict(ck["optimizer_state_dict"])                                  # train.py:217
+    sched2 = torch.optim.lr_scheduler.MultiStepLR(opt2, milestones=[2, 4], gamma=0.1)
+    sched2.load_state_dict(ck["scheduler_state_dict"])
+    assert ck["epoch"] + 1 == 4 and ck["best_acc"] == 0.5
+    for (ka, a), (kb, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert ka == kb and torch.equal(a, b)
+    assert [n for n, _ in src.named_parameters()] == [n for n, _ in dst.named_parameters()]
