@@ -204,6 +204,13 @@ int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const 
                       float* db_part, int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
                       void* stream);
 
+/* Backward of mmb_layernorm_fwd (ln_1 and the patch norms in training).  The statistics are recomputed from x.
+ *   x : the forward's input view (tokens, D), pixel stride x_pixel_stride, dtype x_dtype;  dy: (tokens, D) dense
+ *   dx: (tokens, D) dense in x_dtype;  dgb_part: (mmb_partial_blocks(), 2, D) fp32 partials of dgamma / dbeta.
+ * D % 4 == 0, D <= 512 (wider rows: MMB_ERR_UNSUPPORTED, the caller keeps torch's LayerNorm). */
+int mmb_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgb_part, int64_t tokens,
+                      int D, int64_t x_pixel_stride, float eps, int x_dtype, int dy_dtype, void* stream);
+
 /* Backward of mmb_outnorm_gate_fwd: dout (tokens, D) dense in z_dtype, ymerged from the forward ->
  *   dy (tokens, D) fp32, dz (tokens, D) dense in z_dtype,
  *   dgb_part (mmb_partial_blocks(), 2, D) fp32: [.,0,:] dgamma, [.,1,:] dbeta partials. */

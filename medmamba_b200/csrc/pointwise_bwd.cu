@@ -115,6 +115,97 @@ outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward of the plain LayerNorm (layernorm_fwd_kernel): ln_1, the patch-embed and patch-merging norms in
+// training.  Statistics are recomputed from x (the row is in registers anyway), so the forward saves nothing:
+//   xhat = (x - mean) rstd,  t = dy gamma,  dx = rstd (t - mean(t) - xhat mean(t xhat)),
+//   dgamma += dy xhat,  dbeta += dy   (per-CTA partials, warps added in fixed order: bit-reproducible).
+template <int V, typename x_t, typename dy_t>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, const float* __restrict__ gamma,
+                     x_t* __restrict__ dx, float* __restrict__ part, int64_t tokens, int D, int64_t x_pix, float eps) {
+    __shared__ float4 sred[8][2][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
+    const int C4 = D / 4;
+    float4 g[V], dg[V], db[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c4 = lane + 32 * i;
+        g[i] = c4 < C4 ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i];
+    }
+    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+        float4 v[V], t[V];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            v[i] = c4 < C4 ? load4<x_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[i] = c4 < C4 ? load4<dy_t>(dy + tok * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (lane + 32 * i < C4) {
+                v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        const float rstd = rsqrtf(sq / (float)D + eps);
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (lane + 32 * i < C4) {
+                v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
+                dg[i].x = fmaf(t[i].x, v[i].x, dg[i].x); dg[i].y = fmaf(t[i].y, v[i].y, dg[i].y);
+                dg[i].z = fmaf(t[i].z, v[i].z, dg[i].z); dg[i].w = fmaf(t[i].w, v[i].w, dg[i].w);
+                db[i].x += t[i].x; db[i].y += t[i].y; db[i].z += t[i].z; db[i].w += t[i].w;
+                t[i].x *= g[i].x; t[i].y *= g[i].y; t[i].z *= g[i].z; t[i].w *= g[i].w;  // dy gamma
+                m1 += (t[i].x + t[i].y) + (t[i].z + t[i].w);
+                m2 += (t[i].x * v[i].x + t[i].y * v[i].y) + (t[i].z * v[i].z + t[i].w * v[i].w);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            m1 += __shfl_xor_sync(0xffffffffu, m1, off);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+        }
+        m1 /= (float)D; m2 /= (float)D;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) {
+                float4 o;
+                o.x = rstd * (t[i].x - m1 - v[i].x * m2); o.y = rstd * (t[i].y - m1 - v[i].y * m2);
+                o.z = rstd * (t[i].z - m1 - v[i].z * m2); o.w = rstd * (t[i].w - m1 - v[i].w * m2);
+                store4<x_t>(dx + tok * D + 4 * c4, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        sred[wib][0][lane] = dg[i]; sred[wib][1][lane] = db[i];
+        __syncthreads();
+        if (wib < 2) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < 8; ++w) {
+                const float4 q4 = sred[w][wib][lane];
+                a.x += q4.x; a.y += q4.y; a.z += q4.z; a.w += q4.w;
+            }
+            const int c4 = lane + 32 * i;
+            if (c4 < C4) reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * D)[c4] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // xc = silu(s), s = dwconv(x) + bias.  K1: ds = dxc * silu'(s) (s recomputed), with per-CTA partials of
 // dweight (D, 9) and dbias (D).  The input gradient is then the flipped-kernel convolution of ds
 // (dwconv3x3_silu_kernel<..., ACT=false, FLIP=true> in pointwise.cu).
@@ -242,6 +333,38 @@ extern "C" int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, cons
     if (z_dtype == MMB_BF16) MMB_OB_V(__nv_bfloat16);
 #undef MMB_OB_V
 #undef MMB_OB
+    return MMB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mmb_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgb_part,
+                                 int64_t tokens, int D, int64_t x_pixel_stride, float eps, int x_dtype, int dy_dtype,
+                                 void* stream) {
+    using namespace mmb;
+    if (!x || !dy || !gamma || !dx || !dgb_part) return MMB_ERR_INVALID_ARG;
+    if (tokens < 0 || D <= 0) return MMB_ERR_INVALID_ARG;
+    if (D % 4 != 0 || D > 512 || x_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dgb_part)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define MMB_LB(V, TX, TY)                                                                                        \
+    do {                                                                                                         \
+        if (!al4<TX>(x) || !al4<TX>(dx) || !al4<TY>(dy)) return MMB_ERR_UNSUPPORTED;                             \
+        layernorm_bwd_kernel<V, TX, TY><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const TX*>(x),             \
+            reinterpret_cast<const TY*>(dy), gamma, reinterpret_cast<TX*>(dx), dgb_part, tokens, D,              \
+            x_pixel_stride, eps);                                                                                \
+        return launch_status();                                                                                  \
+    } while (0)
+#define MMB_LB_V(TX, TY)                                                                                         \
+    do {                                                                                                         \
+        if (D <= 128) MMB_LB(1, TX, TY);                                                                         \
+        if (D <= 256) MMB_LB(2, TX, TY);                                                                         \
+        MMB_LB(4, TX, TY);                                                                                       \
+    } while (0)
+    if (x_dtype == MMB_F32 && dy_dtype == MMB_F32) MMB_LB_V(float, float);
+    if (x_dtype == MMB_F32 && dy_dtype == MMB_BF16) MMB_LB_V(float, __nv_bfloat16);
+    if (x_dtype == MMB_BF16 && dy_dtype == MMB_BF16) MMB_LB_V(__nv_bfloat16, __nv_bfloat16);
+    if (x_dtype == MMB_BF16 && dy_dtype == MMB_F32) MMB_LB_V(__nv_bfloat16, float);
+#undef MMB_LB_V
+#undef MMB_LB
     return MMB_ERR_UNSUPPORTED;
 }
 

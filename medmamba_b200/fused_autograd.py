@@ -165,3 +165,48 @@ class ShuffleCatResidualFn(torch.autograd.Function):
                                                     _c_int(dtype_code(g)), _c_int(dtype_code(dleft)), stream_ptr(dev))
         check(st, "mmb_shuffle_cat_residual_bwd")
         return dleft.to(ldt), dssm.to(sdt), g.to(idt)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the channels of a channels-last (B, H, W, C) view with the hand-written forward and
+    backward kernels (ln_1 MedMamba.py:351, the patch norms :75 and :116, in training)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        y = ops.layernorm(x, weight, bias, eps, out_dtype=out_dtype)
+        ctx.save_for_backward(x, weight)
+        ctx.eps = eps
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dev = x.device
+        xv, px, _ = ops._token_view(x)
+        dy = dy.contiguous()
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        g32 = weight.detach().float().contiguous()
+        dx = torch.empty((B, H, W, C), dtype=xv.dtype, device=dev)
+        part = torch.empty((_partial_blocks(), 2, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), timed_launch("layernorm_bwd", f"B={B},L={H * W},C={C}"):
+            st = lib().mmb_layernorm_bwd(ptr(xv), ptr(dy), ptr(g32), ptr(dx), ptr(part), i64(B * H * W), _c_int(C),
+                                         i64(px), ctypes.c_float(ctx.eps), _c_int(dtype_code(xv)),
+                                         _c_int(dtype_code(dy)), stream_ptr(dev))
+        check(st, "mmb_layernorm_bwd")
+        gb = part.sum(0)
+        return dx, gb[0].to(ctx.param_dtypes[0]), gb[1].to(ctx.param_dtypes[1]), None, None
+
+
+def train_layernorm_ok(x: torch.Tensor, ln) -> bool:
+    """The LayerNormFn pair applies: CUDA, autograd needed, plain affine LayerNorm over C % 4 == 0 <= 512, no hooks."""
+    return (x.is_cuda and x.dim() == 4 and isinstance(ln, torch.nn.LayerNorm) and ln.elementwise_affine
+            and ln.bias is not None and len(ln.normalized_shape) == 1 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 512
+            and x.dtype in (torch.float32, torch.bfloat16) and ops.needs_autograd(x, ln.weight, ln.bias)
+            and not ops.has_hooks(ln) and ops.fused_available())
+
+
+def layernorm_train(x: torch.Tensor, ln, out_dtype=None) -> torch.Tensor:
+    return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, out_dtype or x.dtype)

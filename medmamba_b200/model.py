@@ -27,6 +27,16 @@ from .layers import DropPath, trunc_normal_
 from .selective_scan_interface import selective_scan_fn
 
 
+def _train_ln_ok(x, ln) -> bool:
+    from .fused_autograd import train_layernorm_ok
+    return train_layernorm_ok(x, ln)
+
+
+def _train_ln(x, ln, out_dtype):
+    from .fused_autograd import layernorm_train
+    return layernorm_train(x, ln, out_dtype)
+
+
 class PatchEmbed2D(nn.Module):
     """patch_size x patch_size strided conv, NCHW -> NHWC, optional norm (MedMamba.py:54-76)."""
 
@@ -45,6 +55,8 @@ class PatchEmbed2D(nn.Module):
             return x
         if ops.fast_layernorm_ok(x, self.norm):
             return ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype=torch.float32)
+        if getattr(self, "fused", True) and _train_ln_ok(x, self.norm):
+            return _train_ln(x, self.norm, torch.float32)
         return self.norm(x)
 
 
@@ -69,6 +81,8 @@ class PatchMerging2D(nn.Module):
         if ops.fast_layernorm_ok(x, self.norm):
             return self.reduction(ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps,
                                                 out_dtype=ops.autocast_dtype(x.dtype)))
+        if getattr(self, "fused", True) and _train_ln_ok(x, self.norm):
+            return self.reduction(_train_ln(x, self.norm, ops.autocast_dtype(x.dtype)))
         return self.reduction(self.norm(x))
 
 
@@ -286,6 +300,8 @@ class SS_Conv_SSM(nn.Module):
         if ops.fast_layernorm_ok(right, self.ln_1):
             normed = ops.layernorm(right, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps,
                                    out_dtype=ops.autocast_dtype(right.dtype))
+        elif self.self_attention.fused and _train_ln_ok(right, self.ln_1):
+            normed = _train_ln(right, self.ln_1, ops.autocast_dtype(right.dtype))
         else:
             normed = self.ln_1(right)
         ssm = self.drop_path(self.self_attention(normed))

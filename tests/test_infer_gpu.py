@@ -43,6 +43,8 @@ def test_gradcam_style_hooks_on_the_reference_target_layer():
     h1 = target.register_forward_hook(lambda m, i, o: acts.append(o.detach()))
     h2 = target.register_full_backward_hook(lambda m, gi, go: grads.append(go[0].detach()))
     x = torch.randn(1, 3, 64, 64, device="cuda")
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # both paths in true fp32
     try:
         with torch.no_grad():
             net(x)
@@ -62,6 +64,7 @@ def test_gradcam_style_hooks_on_the_reference_target_layer():
         logits_ref[0, logits_ref.argmax()].backward()
     finally:
         h1.remove(); h2.remove()
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     assert torch.allclose(logits, logits_ref, rtol=1e-3, atol=1e-4)
     assert torch.allclose(fused_act, acts[0], rtol=1e-3, atol=1e-4)
     assert torch.allclose(fused_grad, grads[0], rtol=1e-2, atol=1e-5)

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from oracle import medmamba_ref
+from tests.util import assert_close
 from oracle.selective_scan_ref import selective_scan_ref
 
 pytestmark = pytest.mark.gpu
@@ -129,3 +130,32 @@ def test_fused_backward_deterministic_and_bf16():
     for a, p in zip(runs[0], list(m.parameters())):
         err = (p.grad.float() - a).abs().max().item() / max(a.abs().max().item(), 1e-12)
         assert err < 5e-2, err
+
+
+@pytest.mark.parametrize("B,H,W,C,strided,bf16_out", [(2, 5, 7, 48, True, True), (1, 3, 3, 96, False, False),
+                                                      (2, 14, 14, 384, True, True), (3, 4, 4, 512, False, False),
+                                                      (2, 6, 6, 16, True, False)])
+def test_layernorm_fn_gradients(B, H, W, C, strided, bf16_out):
+    """LayerNormFn (mmb_layernorm_fwd / mmb_layernorm_bwd) against torch's LayerNorm autograd in fp64; the
+    strided case is ln_1's input: the right half of the residual stream."""
+    from medmamba_b200.fused_autograd import LayerNormFn
+    g = torch.Generator().manual_seed(C + H)
+    full = torch.randn(B, H, W, 2 * C if strided else C, generator=g)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    dy = torch.randn(B, H, W, C, generator=g)
+    if bf16_out:
+        dy = dy.bfloat16().float()
+    xr = (full[..., C:] if strided else full).double().clone().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-6).backward(dy.double())
+    fc = full.cuda().requires_grad_(True)
+    wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    x = fc[..., C:] if strided else fc
+    y = LayerNormFn.apply(x, wc, bc, 1e-6, torch.bfloat16 if bf16_out else torch.float32)
+    y.backward(dy.cuda().to(y.dtype))
+    gx = fc.grad[..., C:] if strided else fc.grad
+    assert_close(gx, xr.grad, 1e-4, 1e-5, "LayerNormFn dx")
+    assert_close(wc.grad, wr.grad, 1e-4, 1e-4, "LayerNormFn dgamma")
+    assert_close(bc.grad, br.grad, 1e-4, 1e-4, "LayerNormFn dbeta")
+    if strided:
+        assert float(fc.grad[..., :C].abs().max()) == 0.0
