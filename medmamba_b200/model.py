@@ -304,6 +304,19 @@ class SS_Conv_SSM(nn.Module):
             normed = _train_ln(right, self.ln_1, ops.autocast_dtype(right.dtype))
         else:
             normed = self.ln_1(right)
+        if self._cnn_fast_ok(left) and ops.branch_overlap_enabled():
+            # The two branches of a block are independent (MedMamba.py:352-355): the CNN branch (cuDNN, tensor cores
+            # + HBM) runs on a side stream next to the SS2D branch (MUFU-bound scan), filling the SMs the partial
+            # last round of the scan leaves idle.
+            main = torch.cuda.current_stream(input.device)
+            side = ops.side_stream(input.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                left = self._cnn_branch_fast(left)
+            ssm = self.drop_path(self.self_attention(normed))
+            main.wait_stream(side)
+            left.record_stream(main)
+            return ops.shuffle_cat_residual(left, ssm, input)
         ssm = self.drop_path(self.self_attention(normed))
         if self._cnn_fast_ok(left):
             left = self._cnn_branch_fast(left)

@@ -15,6 +15,25 @@ from ._lib import KernelTimer, check, dtype_code, i64, lib, ptr, require_cuda, s
 _c_int = ctypes.c_int
 
 
+_side_streams = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """One extra stream per device for work that is independent of the main stream's (the CNN branch of a block)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device)
+    return st
+
+
+def branch_overlap_enabled() -> bool:
+    """MMB_BRANCH_OVERLAP=0 keeps both branches of a block on one stream (debugging / A-B timing);
+    stream capture (CUDA graphs) also disables the side stream."""
+    import os
+    return os.environ.get("MMB_BRANCH_OVERLAP", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+
+
 def fused_available() -> bool:
     """True when the CUDA library is loadable (it is built on demand; failure raises)."""
     lib()

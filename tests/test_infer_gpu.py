@@ -71,3 +71,20 @@ def test_gradcam_style_hooks_on_the_reference_target_layer():
     with torch.no_grad():                            # hooks removed: the fast path is back
         y = net(x)
     assert torch.allclose(y, logits.detach(), rtol=1e-3, atol=1e-4)
+
+
+def test_branch_overlap_is_bitwise_neutral(monkeypatch):
+    """The CNN branch on a side stream (SS_Conv_SSM.forward) changes scheduling only: same logits bit for bit."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.VSSM(depths=[2, 2], dims=[32, 64], num_classes=4).cuda().eval()
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    outs = {}
+    for flag in ("1", "0", "1"):
+        monkeypatch.setenv("MMB_BRANCH_OVERLAP", flag)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(3):
+                y = net(x)
+        torch.cuda.synchronize()
+        outs.setdefault(flag, []).append(y.float().cpu())
+    assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][0], outs["1"][1])
