@@ -315,7 +315,10 @@ class SS_Conv_SSM(nn.Module):
                 left = self._cnn_branch_fast(left)
             ssm = self.drop_path(self.self_attention(normed))
             main.wait_stream(side)
-            left.record_stream(main)
+            # `left` lives in the side stream's allocator pool and is read by the shuffle kernel on the main stream.
+            # No record_stream: the side stream is used by this method only and every use starts with
+            # side.wait_stream(main), so the pool cannot hand the block out again before that kernel has run
+            # (record_stream's deferred frees made the allocator grow for several steps: cudaMalloc in the loop).
             return ops.shuffle_cat_residual(left, ssm, input)
         ssm = self.drop_path(self.self_attention(normed))
         if self._cnn_fast_ok(left):

@@ -19,11 +19,13 @@ _side_streams = {}
 
 
 def side_stream(device) -> "torch.cuda.Stream":
-    """One extra stream per device for work that is independent of the main stream's (the CNN branch of a block)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """The companion stream of the current stream of `device`, for work that is independent of it (the CNN branch
+    of a block).  One per (device, current stream), so concurrent lanes do not share -- and serialise on -- one."""
+    cur = torch.cuda.current_stream(device)
+    key = (cur.device.index, cur.cuda_stream)
     st = _side_streams.get(key)
     if st is None:
-        st = _side_streams[key] = torch.cuda.Stream(device)
+        st = _side_streams[key] = torch.cuda.Stream(cur.device)
     return st
 
 
