@@ -138,6 +138,13 @@ def cpu_reference_rate(budget_s: float, steps: int, warmup: int, seed: int = 0):
     """images/s of the oracle port of the reference's CPU path.  Returns (value, per-step images, ms_per_step, cores)."""
     import medmamba_b200 as mm
     from oracle import medmamba_ref
+    # every host core: torchrun exports OMP_NUM_THREADS=1, which would leave the CPU arm on a single thread
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     torch.manual_seed(seed)
     sd = {k: v.detach() for k, v in mm.medmamba_t(NUM_CLASSES).state_dict().items()}
     g = torch.Generator().manual_seed(1)
