@@ -16,6 +16,8 @@
 // shared memory with a row pitch of T+4 floats, which makes the per-thread LDS.128 reads of
 // four consecutive steps bank-conflict free.  y overwrites u in place and is stored back
 // coalesced (with the optional silu(z) gate) while the next chunk is loaded.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mmb {
@@ -231,6 +233,186 @@ __global__ void __launch_bounds__(128) scan_fwd_kernel(const ScanFwdParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32, L-contiguous fast path: same ownership and recurrence, but the tiles of chunk c+1 travel global -> shared
+// memory with cp.async (16-byte pieces, zero-filled past the sequence end) while chunk c is computed, into a
+// second set of buffers.  The synchronous kernel above spends its time in the staging phase (ncu, batch 64 stage 1:
+// long-scoreboard stalls 3.2 per issued instruction, 30 % of the stall samples on the STS that parks a loaded
+// value, XU 44 %); here the only exposed global latency is the first chunk's.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int S, int T>
+__global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams p) {
+    constexpr int NT = 128, RT = NT / S, NS = kMaxState / S, JB = NS < 8 ? NS : 8, TP = T + 4, T4 = T / 4;
+    constexpr int BUF = (2 * RT + 2 * kMaxState) * TP;      // floats per buffer set
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int r = tid / S, q = tid % S;
+    const int b = blockIdx.z, g = blockIdx.y;
+    const int row0 = blockIdx.x * RT;
+    const int rows_here = min(RT, p.H - row0);
+    const bool valid = r < rows_here;
+    const int d = g * p.H + row0 + (valid ? r : 0);
+    const float* ub = reinterpret_cast<const float*>(p.u) + (int64_t)b * p.u_bs;
+    const float* db = reinterpret_cast<const float*>(p.delta) + (int64_t)b * p.d_bs;
+    const float* zb = p.z ? reinterpret_cast<const float*>(p.z) + (int64_t)b * p.z_bs : nullptr;
+    float* ob = reinterpret_cast<float*>(p.out) + (int64_t)b * p.o_bs;
+    const float* Bb = reinterpret_cast<const float*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
+    const float* Cb = reinterpret_cast<const float*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+    const bool vec_z = zb && ((reinterpret_cast<uintptr_t>(zb) % 16) == 0) && (p.z_ds % 4 == 0);
+    const bool vec_o = ((reinterpret_cast<uintptr_t>(ob) % 16) == 0) && (p.o_ds % 4 == 0);
+
+    float Ap[NS], h[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int n = q + S * j;
+        Ap[j] = (valid && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+        h[j] = 0.f;
+    }
+    const float Dd = (valid && p.Dv) ? p.Dv[d] : 0.f;
+
+    auto prefetch = [&](int c) {
+        float* base = smem + (c & 1) * BUF;
+        float* su = base, *sd = su + RT * TP, *sB = sd + RT * TP, *sC = sB + kMaxState * TP;
+        const int t0 = c * T, len = min(T, p.L - t0);
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            const bool rok = rr < rows_here;
+            const int64_t dd = g * p.H + row0 + (rok ? rr : 0);
+            const int nb = rok ? max(0, min(4, len - tt)) * 4 : 0;
+            const int ts = nb ? t0 + tt : 0;                       // keep the (unused) source address inside the row
+            cp_async16(su + rr * TP + tt, ub + dd * p.u_ds + ts, nb);
+            cp_async16(sd + rr * TP + tt, db + dd * p.d_ds + ts, nb);
+        }
+        for (int idx = tid; idx < kMaxState * T4; idx += NT) {
+            const int n = idx / T4, tt = (idx % T4) * 4;
+            const int nb = n < p.N ? max(0, min(4, len - tt)) * 4 : 0;
+            const int ts = nb ? t0 + tt : 0;
+            const int nn = n < p.N ? n : 0;
+            cp_async16(sB + n * TP + tt, Bb + (int64_t)nn * p.B_ns + ts, nb);
+            cp_async16(sC + n * TP + tt, Cb + (int64_t)nn * p.C_ns + ts, nb);
+        }
+        cp_async_commit();
+    };
+
+    prefetch(0);
+    for (int c = 0; c < p.nchunks; ++c) {
+        float* base = smem + (c & 1) * BUF;
+        float* su = base, *sd = su + RT * TP, *sB = sd + RT * TP, *sC = sB + kMaxState * TP;
+        const int t0 = c * T, len = min(T, p.L - t0);
+        if (c + 1 < p.nchunks) { prefetch(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        // delta tile in place: + bias, softplus, 0 beyond the sequence (a = 1, b = 0: state untouched)
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            if (rr < rows_here) {
+                float4* ds = reinterpret_cast<float4*>(sd + rr * TP + tt);
+                float4 dv = *ds;
+                const float bs = p.bias ? p.bias[g * p.H + row0 + rr] : 0.f;
+                dv.x += bs; dv.y += bs; dv.z += bs; dv.w += bs;
+                if (p.softplus) { dv.x = softplus_f(dv.x); dv.y = softplus_f(dv.y); dv.z = softplus_f(dv.z); dv.w = softplus_f(dv.w); }
+                if (tt + 0 >= len) dv.x = 0.f;
+                if (tt + 1 >= len) dv.y = 0.f;
+                if (tt + 2 >= len) dv.z = 0.f;
+                if (tt + 3 >= len) dv.w = 0.f;
+                *ds = dv;
+            }
+        }
+        __syncthreads();
+        const int steps = (len + 3) & ~3;
+        for (int tt = 0; tt < steps; tt += 4) {
+            const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + tt);
+            const float4 d4 = *reinterpret_cast<const float4*>(sd + r * TP + tt);
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+            float du[4], y[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { du[s] = dl[s] * uu[s]; y[s] = 0.f; }
+#pragma unroll
+            for (int jb = 0; jb < NS; jb += JB) {
+                float4 Bv[JB], Cv[JB];
+#pragma unroll
+                for (int j = 0; j < JB; ++j) {
+                    const int n = q + S * (jb + j);
+                    Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
+                    Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int j = 0; j < JB; ++j) {
+                        const float bb = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
+                        const float cc = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
+                        const float a = ex2_approx(dl[s] * Ap[jb + j]);
+                        h[jb + j] = fmaf(a, h[jb + j], du[s] * bb);
+                        y[s] = fmaf(h[jb + j], cc, y[s]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = S / 2; off > 0; off >>= 1) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) y[s] += __shfl_xor_sync(0xffffffffu, y[s], off);
+            }
+            if (q == 0) {
+                float4 yo;
+                yo.x = fmaf(Dd, uu[0], y[0]); yo.y = fmaf(Dd, uu[1], y[1]);
+                yo.z = fmaf(Dd, uu[2], y[2]); yo.w = fmaf(Dd, uu[3], y[3]);
+                *reinterpret_cast<float4*>(su + r * TP + tt) = yo;
+            }
+        }
+        __syncthreads();
+        // y of this chunk: shared -> global (coalesced), optional silu(z) gate
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            if (rr < rows_here && tt < len) {
+                const int64_t dd = g * p.H + row0 + rr;
+                float4 y = *reinterpret_cast<const float4*>(su + rr * TP + tt);
+                if (zb) {
+                    const float4 zz = load_row4<float>(zb + dd * p.z_ds + t0, tt, len, vec_z);
+                    y.x *= silu_f(zz.x); y.y *= silu_f(zz.y); y.z *= silu_f(zz.z); y.w *= silu_f(zz.w);
+                }
+                store_row4<float>(ob + dd * p.o_ds + t0, tt, len, vec_o, y);
+            }
+        }
+        __syncthreads();      // the buffer is refilled by the prefetch of chunk c + 2 at the top of the next iteration
+    }
+    if (p.last_state && valid) {
+        float* ls = p.last_state + ((int64_t)b * p.dim + d) * p.N;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) ls[n] = h[j]; }
+    }
+}
+
+template <int S, int T>
+static int launch_scan_fwd_async(const ScanFwdParams& p, cudaStream_t stream) {
+    constexpr size_t smem = 2 * sizeof(float) * (size_t)(2 * (128 / S) + 2 * kMaxState) * (T + 4);
+    auto kern = scan_fwd_async_kernel<S, T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    const int RT = 128 / S;
+    dim3 grid((p.H + RT - 1) / RT, p.G, p.batch);
+    kern<<<grid, 128, smem, stream>>>(p);
+    return launch_status();
+}
+
+// cp.async needs 16-byte aligned, L-contiguous fp32 rows for u, delta, B and C
+static bool async_path_ok(const ScanFwdParams& p, int io_dtype, int bc_dtype) {
+    if (io_dtype != MMB_F32 || bc_dtype != MMB_F32 || p.chunk_state) return false;
+    if (getenv("MMB_SCAN_SYNC")) return false;
+    const auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    if (!al(p.u) || !al(p.delta) || !al(p.Bm) || !al(p.Cm)) return false;
+    if (p.u_ds % 4 || p.u_bs % 4 || p.d_ds % 4 || p.d_bs % 4) return false;
+    if (p.B_ls != 1 || p.C_ls != 1 || p.B_ns % 4 || p.C_ns % 4 || p.B_bs % 4 || p.C_bs % 4 || p.B_gs % 4 || p.C_gs % 4) return false;
+    return true;
+}
+
 template <int S, int T> constexpr size_t scan_fwd_smem() {
     return sizeof(float) * (size_t)(2 * (128 / S) + 2 * kMaxState) * (T + 4);
 }
@@ -314,6 +496,18 @@ extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, co
     const int T = chunk_state ? 16 : chunk_for_split(S);
     p.nchunks = (seqlen + T - 1) / T;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (async_path_ok(p, io_dtype, bc_dtype)) {
+        // chunk length: 16 steps for one lane per row (128 rows per CTA: two buffer sets of 46 KB, 4 CTAs per SM)
+        const int Ta = S == 1 ? 16 : 32;
+        p.nchunks = (seqlen + Ta - 1) / Ta;
+        switch (S) {
+            case 1: return launch_scan_fwd_async<1, 16>(p, st);
+            case 2: return launch_scan_fwd_async<2, 32>(p, st);
+            case 4: return launch_scan_fwd_async<4, 32>(p, st);
+            case 8: return launch_scan_fwd_async<8, 32>(p, st);
+            default: return launch_scan_fwd_async<16, 32>(p, st);
+        }
+    }
     switch (io_dtype) {
         case MMB_F32: return dispatch_bc<float>(p, io_dtype, bc_dtype, S, st);
         case MMB_BF16: return dispatch_bc<__nv_bfloat16>(p, io_dtype, bc_dtype, S, st);
