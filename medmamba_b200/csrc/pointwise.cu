@@ -146,13 +146,14 @@ dwconv3x3_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* _
 #pragma unroll
             for (int j = 0; j < WS + 2; ++j) {
                 const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
-                const uint32_t wds[4] = {nb[dy][j].x, nb[dy][j].y, nb[dy][j].z, nb[dy][j].w};
+                const uint32_t mk = ok ? 0xffffffffu : 0u;        // out-of-image taps: zero the packed words (4 ops, not 8)
+                const uint32_t wds[4] = {nb[dy][j].x & mk, nb[dy][j].y & mk, nb[dy][j].z & mk, nb[dy][j].w & mk};
                 float vv[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // bf16 -> fp32 is a shift: low half is element 2e, high half element 2e + 1
-                    vv[2 * e] = ok ? __uint_as_float(wds[e] << 16) : 0.f;
-                    vv[2 * e + 1] = ok ? __uint_as_float(wds[e] & 0xffff0000u) : 0.f;
+                    vv[2 * e] = __uint_as_float(wds[e] << 16);
+                    vv[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u);
                 }
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
