@@ -111,6 +111,12 @@ int mmb_ss2d_core_dt_pad(int dt_rank);
 /* Blocks per direction of the training geometry (host only): the third extent of `hsave`. */
 int mmb_ss2d_core_train_blocks(int H, int W);
 
+/* Launch geometry mmb_ss2d_core_fwd would use for this problem (host only, nothing is launched): lanes per channel
+ * (1, 2 or 4), channels per CTA (a multiple of 32 / lanes, <= 256) and the number of channel tiles.  The choice comes
+ * from a cost model fitted to measurements; exposed for tests and for capacity planning. */
+int mmb_ss2d_core_plan(int batch, int H, int W, int D, int* lanes_per_channel, int* channels_per_cta,
+                       int* channel_tiles);
+
 /* Four-direction selective scan of SS2D.forward_corev0 in one launch.  Replaces the cross-scan
  * (MedMamba.py:256-257), the dt_proj einsum and its copy (:262, :266), selective_scan_fn (:273-279,
  * delta_softplus=True, delta_bias=dt_projs_bias, z=None) and the flips / transposes of the

@@ -456,6 +456,17 @@ extern "C" int mmb_ss2d_core_train_blocks(int H, int W) {
     return g.nblocks_max();
 }
 
+extern "C" int mmb_ss2d_core_plan(int batch, int H, int W, int D, int* lanes_per_channel, int* channels_per_cta,
+                                  int* channel_tiles) {
+    using namespace mmb;
+    if (batch <= 0 || H <= 0 || W <= 0 || D <= 0 || !lanes_per_channel || !channels_per_cta || !channel_tiles)
+        return MMB_ERR_INVALID_ARG;
+    CorePlan pl;
+    if (!plan_core_tiles(batch, D, H * W, pl)) return MMB_ERR_UNSUPPORTED;
+    *lanes_per_channel = pl.S; *channels_per_cta = pl.CT; *channel_tiles = pl.tiles;
+    return MMB_OK;
+}
+
 extern "C" int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
                                  const float* A, const float* Ds, float* ydir, float* hsave,
                                  int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype, void* stream) {

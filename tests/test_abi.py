@@ -49,3 +49,24 @@ def test_cuda_ops_refuse_cpu_tensors():
     z = torch.zeros
     with pytest.raises(RuntimeError):
         selective_scan_fn(z(1, 4, 3), z(1, 4, 3), -torch.ones(4, 16), z(1, 4, 16, 3), z(1, 4, 16, 3))
+
+
+def test_core_plan_is_consistent_on_the_bench_shapes():
+    """mmb_ss2d_core_plan (host only): tiles cover D, CTAs are whole warps, MedMamba-T at batch 256..1024 runs one lane
+    per channel with 96 / 96 / 128 / 128 channels per CTA on a 148-SM part (the measured optimum, profiles/README.md)."""
+    from medmamba_b200 import _lib
+    h = _lib.lib()
+    got = {}
+    for batch in (1, 8, 64, 256, 1024):
+        for (H, D) in ((56, 96), (28, 192), (14, 384), (7, 768), (128, 96)):
+            S, CT, tiles = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            st = h.mmb_ss2d_core_plan(ctypes.c_int(batch), ctypes.c_int(H), ctypes.c_int(H), ctypes.c_int(D),
+                                      ctypes.byref(S), ctypes.byref(CT), ctypes.byref(tiles))
+            assert st == 0
+            assert S.value in (1, 2, 4) and CT.value * tiles.value >= D and (CT.value * S.value) % 32 == 0
+            assert CT.value <= 256 and CT.value * S.value <= 384 and (tiles.value - 1) * CT.value < D
+            got[(batch, H, D)] = (S.value, CT.value, tiles.value)
+    for batch in (256, 1024):
+        plan = [got[(batch, H, D)][:2] for (H, D) in ((56, 96), (28, 192), (14, 384), (7, 768))]
+        assert plan == [(1, 96), (1, 96), (1, 128), (1, 128)], got
+    assert h.mmb_ss2d_core_plan(ctypes.c_int(0), ctypes.c_int(1), ctypes.c_int(1), ctypes.c_int(4), None, None, None) == -1
