@@ -319,3 +319,64 @@ def test_block_cnn_fast_path_matches_module_path(dim, H, W):
     assert_close(fast, slow, 1e-4, 1e-5, "CNN fast path")
     assert_close(fast2, slow2, 1e-4, 1e-5, "CNN fast path after a weight update")
     assert not torch.allclose(fast, fast2)
+
+
+def _core_inputs_gpu(B, H, W, D, R, seed):
+    from medmamba_b200 import ops
+    N = 16
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rp = ops.dt_pad(R)
+    xc = 0.3 * torch.randn(B, H, W, D, device="cuda", generator=g)
+    proj = 0.2 * torch.randn(B, H, W, 4, 32 + rp, device="cuda", generator=g)
+    proj[..., 32 + R:] = 0
+    Wdt = torch.randn(4, D, R, device="cuda", generator=g) * R ** -0.5
+    bias = torch.randn(4, D, device="cuda", generator=g) - 3.0
+    A = -torch.exp(0.3 * torch.randn(4 * D, N, device="cuda", generator=g)) * torch.arange(1, N + 1, device="cuda")
+    Ds = torch.randn(4 * D, device="cuda", generator=g)
+    return xc, proj, Wdt, bias, A.contiguous(), Ds, N
+
+
+def _permute_dirs(proj, Wdt, bias, A, Ds, perm, D):
+    idx = torch.tensor(perm, device=proj.device)
+    return (proj.index_select(3, idx).contiguous(), Wdt.index_select(0, idx).contiguous(), bias.index_select(0, idx).contiguous(),
+            A.view(4, D, -1).index_select(0, idx).reshape(4 * D, -1).contiguous(), Ds.view(4, D).index_select(0, idx).reshape(-1).contiguous())
+
+
+@pytest.mark.parametrize("B,H,W,D,R", [(64, 56, 56, 96, 3), (3, 40, 72, 192, 6), (2, 9, 31, 40, 3), (256, 14, 14, 384, 12)])
+def test_core_index_maps_bit_exact_under_transpose_and_flip(B, H, W, D, R):
+    """Size-independent property at the full stage shapes: transposing the token grid turns
+    the row-order directions into the column-order ones, reversing it turns forward into backward.  With the
+    per-direction parameters permuted the same way, every direction runs the same sequence of operations on the
+    same numbers, so the outputs must agree BIT FOR BIT at the mapped positions -- whatever block geometry,
+    ring path (row boxes / column boxes) or group mode the kernel picks for either layout."""
+    from medmamba_b200 import ops
+    xc, proj, Wdt, bias, A, Ds, N = _core_inputs_gpu(B, H, W, D, R, seed=H * W + D)
+    y = ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R)
+    # transpose: (h, w) -> (w, h); directions 0 <-> 1, 2 <-> 3
+    perm = [1, 0, 3, 2]
+    pT, WT, bT, AT, DT = _permute_dirs(proj.transpose(1, 2).contiguous(), Wdt, bias, A, Ds, perm, D)
+    yT = ops.ss2d_core(xc.transpose(1, 2).contiguous(), pT, WT, bT, AT, DT, N, R)
+    want = y.transpose(1, 2).index_select(3, torch.tensor(perm, device="cuda"))
+    assert torch.equal(yT, want), f"transpose: max diff {(yT - want).abs().max().item()}"
+    # reversal: p -> L-1-p; directions 0 <-> 2, 1 <-> 3
+    perm = [2, 3, 0, 1]
+    pR, WR, bR, AR, DR = _permute_dirs(proj.flip(1, 2).contiguous(), Wdt, bias, A, Ds, perm, D)
+    yR = ops.ss2d_core(xc.flip(1, 2).contiguous(), pR, WR, bR, AR, DR, N, R)
+    want = y.flip(1, 2).index_select(3, torch.tensor(perm, device="cuda"))
+    assert torch.equal(yR, want), f"reversal: max diff {(yR - want).abs().max().item()}"
+
+
+def test_core_is_linear_in_u_at_the_bench_shape():
+    """For fixed proj (delta, B, C) the scan is linear in u: y(a u1 + b u2) = a y(u1) + b y(u2), checked at the
+    stage-1 shape of the default bench batch share (256 images) -- no oracle needed at this size."""
+    from medmamba_b200 import ops
+    B, H, W, D, R = 256, 56, 56, 96, 3
+    xc, proj, Wdt, bias, A, Ds, N = _core_inputs_gpu(B, H, W, D, R, seed=7)
+    x2 = torch.randn_like(xc) * 0.3
+    y1 = ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R)
+    y2 = ops.ss2d_core(x2, proj, Wdt, bias, A, Ds, N, R)
+    y3 = ops.ss2d_core(0.5 * xc - 2.0 * x2, proj, Wdt, bias, A, Ds, N, R)
+    want = 0.5 * y1 - 2.0 * y2
+    scale = want.abs().max().item()
+    assert ((y3 - want).abs().max().item()) <= 2e-5 * scale
+    assert torch.isfinite(y3).all()
