@@ -332,25 +332,44 @@ __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams
             float du[4], y[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) { du[s] = dl[s] * uu[s]; y[s] = 0.f; }
+            if constexpr (NS >= 2) {
+                // two states per packed FMUL2 / FFMA2 (one issue slot for two fp32 operations), two y accumulators
+                float y2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int jb = 0; jb < NS; jb += JB) {
-                float4 Bv[JB], Cv[JB];
-#pragma unroll
-                for (int j = 0; j < JB; ++j) {
-                    const int n = q + S * (jb + j);
-                    Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
-                    Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
-                }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int jb = 0; jb < NS; jb += JB) {
+                    float4 Bv[JB], Cv[JB];
 #pragma unroll
                     for (int j = 0; j < JB; ++j) {
-                        const float bb = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
-                        const float cc = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
-                        const float a = ex2_approx(dl[s] * Ap[jb + j]);
-                        h[jb + j] = fmaf(a, h[jb + j], du[s] * bb);
-                        y[s] = fmaf(h[jb + j], cc, y[s]);
+                        const int n = q + S * (jb + j);
+                        Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
+                        Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
                     }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                        for (int j = 0; j < JB; j += 2) {
+                            const float b0 = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
+                            const float b1 = s == 0 ? Bv[j + 1].x : s == 1 ? Bv[j + 1].y : s == 2 ? Bv[j + 1].z : Bv[j + 1].w;
+                            const float c0 = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
+                            const float c1 = s == 0 ? Cv[j + 1].x : s == 1 ? Cv[j + 1].y : s == 2 ? Cv[j + 1].z : Cv[j + 1].w;
+                            float x0, x1, w0, w1;
+                            mul2(x0, x1, dl[s], dl[s], Ap[jb + j], Ap[jb + j + 1]);
+                            mul2(w0, w1, du[s], du[s], b0, b1);
+                            const float a0 = ex2_approx(x0), a1 = ex2_approx(x1);
+                            fma2(h[jb + j], h[jb + j + 1], a0, a1, h[jb + j], h[jb + j + 1], w0, w1);
+                            fma2(y[s], y2[s], h[jb + j], h[jb + j + 1], c0, c1, y[s], y2[s]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) y[s] += y2[s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float bb = sB[q * TP + tt + s], cc = sC[q * TP + tt + s];
+                    const float a = ex2_approx(dl[s] * Ap[0]);
+                    h[0] = fmaf(a, h[0], du[s] * bb);
+                    y[s] = fmaf(h[0], cc, y[s]);
                 }
             }
 #pragma unroll
