@@ -417,12 +417,8 @@ static int launch_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const flo
 template <int RP, typename xc_t>
 static int dispatch_core_s(CorePlan& pl, CoreFwdParams& p, const void* xc, const float* proj, cudaStream_t st) {
     switch (pl.S) {
-        case 1: {
-            static const int mb = getenv("MMB_CORE_MB") ? atoi(getenv("MMB_CORE_MB")) : 2;
-            if (mb == 3) return launch_core<1, RP, xc_t, 3>(pl, p, xc, proj, st);
-            if (mb == 1) return launch_core<1, RP, xc_t, 1>(pl, p, xc, proj, st);
-            return launch_core<1, RP, xc_t, 2>(pl, p, xc, proj, st);
-        }
+        // one lane per channel: 128-register budget (2 CTAs of 256 threads; the register sweep is in profiles/README.md)
+        case 1: return launch_core<1, RP, xc_t, 2>(pl, p, xc, proj, st);
         case 2: return launch_core<2, RP, xc_t>(pl, p, xc, proj, st);
         default: return launch_core<4, RP, xc_t>(pl, p, xc, proj, st);
     }
