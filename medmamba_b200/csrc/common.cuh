@@ -83,6 +83,40 @@ __device__ __forceinline__ void softplus2_f(float& r0, float& r1, float x0, floa
     r1 = x1 > 20.0f ? x1 : q1;
 }
 
+// Four softplus evaluations for one warp-uniform group of steps.  The lg2 branch of softplus_f is needed only when
+// e^x >= 1/8; with MedMamba's dt range (softplus^-1 of 1e-3 .. 1e-1 plus a small projection) that is rare, so the
+// warp votes once per group and skips the four MUFU.LG2 (the scan kernel is bound by the MUFU rate) when no lane
+// needs them.  Bit-identical to softplus_f in both branches.
+__device__ __forceinline__ void softplus4_vote(float (&r)[4], const float (&x)[4]) {
+    float v[4], s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = ex2_approx(x[i] * kLog2e);
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+        float s0, s1;
+        fma2(s0, s1, v[i], v[i + 1], -0.125f, -0.125f, 1.0f / 7.0f, 1.0f / 7.0f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, -1.0f / 6.0f, -1.0f / 6.0f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, 0.2f, 0.2f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, -0.25f, -0.25f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, 1.0f / 3.0f, 1.0f / 3.0f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, -0.5f, -0.5f);
+        fma2(s0, s1, v[i], v[i + 1], s0, s1, 1.0f, 1.0f);
+        mul2(s[i], s[i + 1], v[i], v[i + 1], s0, s1);
+    }
+    const bool need = !(v[0] < 0.125f) || !(v[1] < 0.125f) || !(v[2] < 0.125f) || !(v[3] < 0.125f);   // NaN -> slow path
+    if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float big = lg2_approx(1.0f + v[i]) * kLn2;
+            const float q = v[i] < 0.125f ? s[i] : big;
+            r[i] = x[i] > 20.0f ? x[i] : q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = s[i];
+    }
+}
+
 // d softplus / dx = sigmoid(x) (1 above the threshold, as torch's backward does).
 __device__ __forceinline__ float sigmoid_f(float x) {
     return rcp_approx(1.0f + ex2_approx(-x * kLog2e));

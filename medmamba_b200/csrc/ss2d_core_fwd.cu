@@ -31,6 +31,7 @@
 namespace mmb {
 
 constexpr int kCoreStages = 4;
+constexpr bool kVoteSoftplus = true;     // one warp vote per group of 4 steps skips the lg2 half of softplus
 constexpr bool kPackSoftplus = true;    // A/B on B200: packed pairs 0.9% faster over the four stage shapes
 constexpr int kCoreStageBytes = 16 * 1024;
 
@@ -209,7 +210,9 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 }
                 raw[m] = acc0 + acc1;
             }
-            if (OWN % 2 == 0 && kPackSoftplus) {
+            if constexpr (OWN == 4 && kVoteSoftplus) {
+                softplus4_vote(down, raw);
+            } else if (OWN % 2 == 0 && kPackSoftplus) {
 #pragma unroll
                 for (int m = 0; m < OWN; m += 2) softplus2_f(down[m], down[m + 1], raw[m], raw[m + 1]);
             } else {
