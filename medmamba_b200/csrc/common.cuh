@@ -117,6 +117,22 @@ __device__ __forceinline__ void softplus4_vote(float (&r)[4], const float (&x)[4
     }
 }
 
+// softplus(x) and its derivative sigmoid(x) = e^x / (1 + e^x) from one e^x (three MUFU operations instead of four).
+__device__ __forceinline__ void softplus_sigmoid_f(float x, float& sp, float& sg) {
+    const float v = ex2_approx(x * kLog2e);
+    const float big = lg2_approx(1.0f + v) * kLn2;
+    float s = fmaf(v, -0.125f, 1.0f / 7.0f);
+    s = fmaf(v, s, -1.0f / 6.0f);
+    s = fmaf(v, s, 0.2f);
+    s = fmaf(v, s, -0.25f);
+    s = fmaf(v, s, 1.0f / 3.0f);
+    s = fmaf(v, s, -0.5f);
+    s = fmaf(v, s, 1.0f);
+    const float r = v < 0.125f ? v * s : big;
+    sp = x > 20.0f ? x : r;
+    sg = x > 20.0f ? 1.0f : v * rcp_approx(1.0f + v);
+}
+
 // d softplus / dx = sigmoid(x) (1 above the threshold, as torch's backward does).
 __device__ __forceinline__ float sigmoid_f(float x) {
     return rcp_approx(1.0f + ex2_approx(-x * kLog2e));

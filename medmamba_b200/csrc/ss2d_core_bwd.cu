@@ -185,8 +185,10 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 fma2(acc0, acc1, Wd[4 * r4 + 2], Wd[4 * r4 + 3], v.z, v.w, acc0, acc1);
             }
             const float raw = acc0 + acc1;
-            stp[(tl * 3 + 0) * 32] = ok ? softplus_f(raw) : 0.f;
-            stp[(tl * 3 + 1) * 32] = ok ? (raw > 20.f ? 1.f : sigmoid_f(raw)) : 0.f;
+            float sp, sg;
+            softplus_sigmoid_f(raw, sp, sg);
+            stp[(tl * 3 + 0) * 32] = ok ? sp : 0.f;
+            stp[(tl * 3 + 1) * 32] = ok ? sg : 0.f;
             stp[(tl * 3 + 2) * 32] = ok ? to_f<xc_t>(xs[sl * p.CT]) : 0.f;
         }
         // one forward step of all 16 states; `park` stores h_{t-1} into history slab `hslot`
