@@ -17,6 +17,8 @@
 // per-thread accumulators, one partial per batch element.  No float atomics: bit-reproducible.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "core_geom.cuh"
 #include "tma.cuh"
@@ -215,8 +217,9 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
         };
         // reverse step tl, history slab hslot
-        auto reverse = [&](const int tl, const int hslot) {
-            const bool ok = tl < nsteps;
+        // FULLB: the block has all TB steps, so no step is masked (the selects on `ok` fold away)
+        auto reverse = [&](auto full_tag, const int tl, const int hslot) {
+            const bool ok = decltype(full_tag)::value || tl < nsteps;
             const int sl = slot_of(tl);
             const float4* bp = reinterpret_cast<const float4*>(ps + sl * CP) + q * (NS / 4);
             const float dy = ok ? dys[sl * p.CT] : 0.f;
@@ -306,13 +309,15 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             for (int tl = 0; tl < kHalf; ++tl) advance(h, tl, false, 0);
             for (int tl = kHalf; tl < TB; ++tl) advance(h, tl, true, tl - kHalf);
             __syncwarp();
-            for (int tl = TB - 1; tl >= kHalf; --tl) reverse(tl, tl - kHalf);
+            if (nsteps == TB) { for (int tl = TB - 1; tl >= kHalf; --tl) reverse(std::true_type{}, tl, tl - kHalf); }
+            else { for (int tl = TB - 1; tl >= kHalf; --tl) reverse(std::false_type{}, tl, tl - kHalf); }
         }
         // first half
         load_checkpoint(h);
         for (int tl = 0; tl < kHalf; ++tl) advance(h, tl, true, tl);
         __syncwarp();
-        for (int tl = kHalf - 1; tl >= 0; --tl) reverse(tl, tl);
+        if (nsteps >= kHalf) { for (int tl = kHalf - 1; tl >= 0; --tl) reverse(std::true_type{}, tl, tl); }
+        else { for (int tl = kHalf - 1; tl >= 0; --tl) reverse(std::false_type{}, tl, tl); }
 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
