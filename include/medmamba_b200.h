@@ -32,10 +32,15 @@ extern "C" {
 
 typedef enum { MMB_F32 = 0, MMB_BF16 = 1, MMB_F16 = 2 } mmb_dtype;
 
-#define MMB_ABI_VERSION 1
+#define MMB_ABI_VERSION 2
 
 /* ABI version of the loaded library (host only, no CUDA call). */
 int mmb_abi_version(void);
+
+/* SHA-256 (hex) of the sources and compiler flags this library was built from, or "unknown" (host only).
+ * The Python loader compares it with the digest of the sources next to it and refuses a stale library: ctypes
+ * checks neither arity nor types, so an old binary behind new call sites would corrupt memory silently. */
+const char* mmb_source_digest(void);
 
 /* Static description of a status code (host only). */
 const char* mmb_status_string(int status);

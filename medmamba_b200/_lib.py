@@ -15,7 +15,7 @@ from . import build as _build
 
 MMB_F32, MMB_BF16, MMB_F16 = 0, 1, 2
 _DTYPES = {torch.float32: MMB_F32, torch.bfloat16: MMB_BF16, torch.float16: MMB_F16}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -26,23 +26,42 @@ class MedMambaLibraryError(RuntimeError):
 
 
 def lib() -> ctypes.CDLL:
-    """The loaded library (built on first use if the in-tree .so is absent or stale)."""
+    """The loaded library (built on first use if the in-tree .so is absent or stale).
+
+    No silent fallback: when the sources changed and the rebuild fails, this raises even if an older .so is lying
+    around (ctypes checks neither arity nor types, so stale kernels behind new call sites corrupt memory).  The
+    library carries the digest of the sources it was built from (``mmb_source_digest``); a mismatch raises too.
+    ``MMB_ALLOW_PREBUILT=1`` is the explicit opt-in for running a prebuilt library without a toolchain."""
     global _lib
     if _lib is None:
         with _lock:
             if _lib is None:
                 path = _build.LIB_PATH
+                allow_prebuilt = os.environ.get("MMB_ALLOW_PREBUILT", "0") == "1"
                 if not _build.up_to_date():
                     try:
                         path = _build.build()
-                    except Exception as e:  # no silent fallback: the product path needs the extension
-                        if not os.path.exists(path):
+                    except Exception as e:
+                        if not (allow_prebuilt and os.path.exists(path)):
                             raise MedMambaLibraryError(
-                                f"libmedmamba_b200.so is missing and could not be built: {e}") from e
+                                f"libmedmamba_b200.so is missing or stale and could not be rebuilt: {e} "
+                                "(set MMB_ALLOW_PREBUILT=1 to load an existing library anyway)") from e
+                        import warnings
+                        warnings.warn(f"medmamba_b200: rebuild failed ({e}); loading the PREBUILT library at {path} "
+                                      "because MMB_ALLOW_PREBUILT=1", RuntimeWarning)
                 handle = ctypes.CDLL(path)
                 handle.mmb_status_string.restype = ctypes.c_char_p
                 if handle.mmb_abi_version() != ABI_VERSION:
                     raise MedMambaLibraryError("libmedmamba_b200.so has a different ABI version; rebuild it")
+                try:
+                    handle.mmb_source_digest.restype = ctypes.c_char_p
+                    built_from = handle.mmb_source_digest().decode()
+                except AttributeError:
+                    built_from = "absent"
+                if built_from != _build._digest() and not allow_prebuilt:
+                    raise MedMambaLibraryError(
+                        f"libmedmamba_b200.so was built from other sources (digest {built_from[:12]}...); "
+                        "run python -m medmamba_b200.build --force")
                 _lib = handle
     return _lib
 

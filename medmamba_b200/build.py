@@ -70,9 +70,14 @@ def _build_locked(verbose: bool) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
     procs = []
+    digest = _digest()
     for src in sources():
         obj = os.path.join(HERE, "_build", os.path.basename(src)[:-3] + ".o")
         cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-I", INCLUDE, "-c", src, "-o", obj]
+        if os.path.basename(src) == "api.cu":
+            # the digest of the sources this library was built from, queryable as mmb_source_digest():
+            # the loader refuses a library whose digest differs from the sources next to it
+            cmd.insert(1, f'-DMMB_SOURCE_DIGEST="{digest}"')
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -90,7 +95,7 @@ def _build_locked(verbose: bool) -> str:
     if verbose:
         print("\n".join(log))
     with open(STAMP, "w") as f:
-        f.write(_digest())
+        f.write(digest)
     return LIB_PATH
 
 

@@ -1,7 +1,13 @@
 // Host-only entry points of the C ABI (no CUDA calls).
 #include "common.cuh"
 
+#ifndef MMB_SOURCE_DIGEST
+#define MMB_SOURCE_DIGEST "unknown"
+#endif
+
 extern "C" int mmb_abi_version(void) { return MMB_ABI_VERSION; }
+
+extern "C" const char* mmb_source_digest(void) { return MMB_SOURCE_DIGEST; }
 
 extern "C" const char* mmb_status_string(int status) {
     if (status == MMB_OK) return "ok";

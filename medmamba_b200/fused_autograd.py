@@ -101,31 +101,46 @@ class CoreNormGateFn(torch.autograd.Function):
         dy = torch.empty((B, H, W, D), **f32)
         dz = torch.empty((B, H, W, D), dtype=zv.dtype, device=dev)
         gb_part = torch.empty((_partial_blocks(), 2, D), **f32)
-        tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(D))
-        dudir = torch.empty((B, H, W, 4, D), **f32)
-        dproj_p = torch.empty((tiles, B, H, W, 4, 32 + rp), **f32)
-        dA_p = torch.empty((B, 4 * D, N), **f32)
-        dW_p = torch.empty((B, 4 * D, rp), **f32)
-        dD_p = torch.empty((B, 4 * D), **f32)
-        db_p = torch.empty((B, 4 * D), **f32)
         with torch.cuda.device(dev):
             with timed_launch("outnorm_gate_bwd", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_outnorm_gate_bwd(ptr(dout), ptr(merged), ptr(zv), ptr(g32), ptr(b32), ptr(dy), ptr(dz),
                                                 ptr(gb_part), i64(B * H * W), _c_int(D), i64(z_px), ctypes.c_float(eps),
                                                 _c_int(dtype_code(zv)), stream_ptr(dev))
             check(st, "mmb_outnorm_gate_bwd")
-            with timed_launch("ss2d_core_bwd", f"B={B},L={H * W},D={D},R={R}"):
-                st = lib().mmb_ss2d_core_bwd(ptr(xc), ptr(proj), ptr(dy), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds),
-                                             ptr(hsave), ptr(dudir), ptr(dproj_p), ptr(dA_p), ptr(dW_p), ptr(dD_p),
-                                             ptr(db_p), _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(N), _c_int(R), _c_int(rp),
-                                             _c_int(dtype_code(xc)), stream_ptr(dev))
-            check(st, "mmb_ss2d_core_bwd")
+        dudir, dproj, dA, dWdt, dD, db = core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, N, R)
         gb = gb_part.sum(0)
         dxc = dudir.sum(3).to(xc.dtype)
-        dproj = dproj_p[0] if tiles == 1 else dproj_p.sum(0)
-        dWdt = dW_p.sum(0)[:, :R].reshape(4, D, R)
-        return (dxc, dproj, dz, dWdt.to(wdt_t), db_p.sum(0).view(4, D).to(b_t), dA_p.sum(0).to(a_t),
-                dD_p.sum(0).to(d_t), gb[0].to(gamma.dtype), gb[1].to(beta.dtype), None, None, None)
+        return (dxc, dproj, dz, dWdt.to(wdt_t), db.to(b_t), dA.to(a_t), dD.to(d_t), gb[0].to(gamma.dtype),
+                gb[1].to(beta.dtype), None, None, None)
+
+
+def core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, d_state: int, dt_rank: int):
+    """mmb_ss2d_core_bwd with its partial sums added up (deterministic: ``torch.sum`` over the partial axis).
+    xc (B, H, W, D) fp32 / bf16, proj (B, H, W, 4, 32+RP) fp32, dy (B, H, W, D) fp32 = gradient of the merged sum,
+    hsave as written by ``ops.ss2d_core(..., save_states=True)``  ->
+    dudir (B, H, W, 4, D), dproj (B, H, W, 4, 32+RP), dA (4D, N), dWdt (4, D, R), dDs (4D,), d dt_bias (4, D), fp32."""
+    B, H, W, D = xc.shape
+    dev = xc.device
+    N, R = d_state, dt_rank
+    f32 = dict(dtype=torch.float32, device=dev)
+    rp = ops.dt_pad(R)
+    if proj.dtype != torch.float32 or dy.dtype != torch.float32 or xc.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("core_bwd: proj and dy must be float32, xc float32 or bfloat16")
+    tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(D))
+    dudir = torch.empty((B, H, W, 4, D), **f32)
+    dproj_p = torch.empty((tiles, B, H, W, 4, 32 + rp), **f32)
+    dA_p = torch.empty((B, 4 * D, N), **f32)
+    dW_p = torch.empty((B, 4 * D, rp), **f32)
+    dD_p = torch.empty((B, 4 * D), **f32)
+    db_p = torch.empty((B, 4 * D), **f32)
+    with torch.cuda.device(dev), timed_launch("ss2d_core_bwd", f"B={B},L={H * W},D={D},R={R}"):
+        st = lib().mmb_ss2d_core_bwd(ptr(xc), ptr(proj), ptr(dy), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds),
+                                     ptr(hsave), ptr(dudir), ptr(dproj_p), ptr(dA_p), ptr(dW_p), ptr(dD_p),
+                                     ptr(db_p), _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(N), _c_int(R), _c_int(rp),
+                                     _c_int(dtype_code(xc)), stream_ptr(dev))
+    check(st, "mmb_ss2d_core_bwd")
+    dproj = dproj_p[0] if tiles == 1 else dproj_p.sum(0)
+    return (dudir, dproj, dA_p.sum(0), dW_p.sum(0)[:, :R].reshape(4, D, R), dD_p.sum(0), db_p.sum(0).view(4, D))
 
 
 def ss2d_inner_train(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
@@ -140,7 +155,8 @@ def ss2d_inner_train(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_proj
         proj = _MmF32Out.apply(xc.view(-1, D), w_packed).view(B, H, W, 4, -1)
     else:
         xc = DwConvSiluFn.apply(x, conv_w, conv_b, torch.float32)
-        proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+        with torch.autocast("cuda", enabled=False):      # fp32 x_proj whatever the caller's autocast dtype is
+            proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
     A = -torch.exp(A_logs.float())
     return CoreNormGateFn.apply(xc, proj, z, dt_projs_weight, dt_projs_bias, A, Ds.float(), norm_w, norm_b, eps,
                                 d_state, dt_rank)

@@ -6,7 +6,7 @@ Same class names, constructor arguments, parameter names / shapes and ``state_di
 ``load_state_dict`` and consumers that walk the module tree (``test.py:101``) keep working.
 Parameter initialisation draws from the RNG in the same order as the reference, so
 ``torch.manual_seed(s); VSSM(...)`` yields the same random-init weights (checked in
-tests/test_model_cpu.py against the unmodified reference).
+tests/test_oracle.py against the unmodified reference).
 
 What differs is what runs between ``in_proj`` and ``out_proj`` and after the concat: on CUDA the
 hand-written sm_100a kernels behind the C ABI (``medmamba_b200.ops``).  The ``in_proj`` /
@@ -215,7 +215,8 @@ class SS2D(nn.Module):
         return self.out_proj(y.to(xz.dtype) if y.dtype != xz.dtype else y)
 
     def forward(self, x: torch.Tensor, **kwargs):
-        use_fused = (self.fused and x.is_cuda and self.d_conv == 3 and ops.fused_available()
+        use_fused = (self.fused and x.is_cuda and self.d_conv == 3
+                     and ops.fused_supported(self.d_state, self.dt_rank, self.d_inner) and ops.fused_available()
                      and not ops.has_hooks(self.conv2d, self.act, self.out_norm))
         out = self._forward_fused(x) if use_fused else self._forward_reference_order(x)
         return out if self.dropout is None else self.dropout(out)
@@ -259,7 +260,10 @@ class SS_Conv_SSM(nn.Module):
         gathering the left half (mmb_affine_cast_fwd); the two BNs that follow convolutions fold into those
         convolutions' weights and biases exactly.  Invalidated when any parameter / buffer changes."""
         seq = self.conv33conv33conv11
-        key = (dtype,) + tuple(t._version for m in seq for t in list(m.parameters()) + list(m.buffers()))
+        # _version follows in-place updates (optimizer steps, load_state_dict); data_ptr / device follow rebinding
+        # through `.data` (EMA weight swaps, net.to(other_device) after a forward)
+        key = (dtype,) + tuple((t._version, t.data_ptr(), t.device) for m in seq
+                               for t in list(m.parameters()) + list(m.buffers()))
         cached = getattr(self, "_cnn_cache", None)
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -326,7 +330,7 @@ class SS_Conv_SSM(nn.Module):
         else:
             # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
             left = self.conv33conv33conv11(left.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
-        if input.is_cuda and ops.fused_available():
+        if input.is_cuda and ops.shuffle_supported(ssm.shape[-1]) and ops.fused_available():
             return ops.shuffle_cat_residual(left, ssm, input)
         return channel_shuffle(torch.cat((left, ssm), dim=-1), groups=2) + input
 

@@ -42,6 +42,17 @@ def fused_available() -> bool:
     return True
 
 
+def fused_supported(d_state: int, dt_rank: int, d_inner: int) -> bool:
+    """Shape limits of the fused SS2D kernels: d_state <= 16, dt_rank <= 32, d_inner % 4 == 0.  Configurations the
+    reference can construct outside them (VSSM(d_state=None, dims=[128, ...]) gives d_state 22) take the
+    reference-order path, whose scan still runs in mmb_scan_fwd when d_state <= 16 and raises otherwise."""
+    return d_state <= 16 and dt_rank <= 32 and d_inner % 4 == 0
+
+
+def shuffle_supported(c: int) -> bool:
+    return c % 4 == 0
+
+
 # ------------------------------------------------------------------------ reference-order helpers
 def cross_scan(x: torch.Tensor) -> torch.Tensor:
     """(B, D, H, W) -> (B, 4, D, L): row-major, column-major and both reversed (MedMamba.py:256-257)."""
@@ -97,7 +108,17 @@ def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int, save_st
     dev = require_cuda(xc, proj, Wdt, dt_bias, A, Ds)
     B, H, W, D = xc.shape
     rp = dt_pad(dt_rank)
-    assert proj.shape == (B, H, W, 4, 32 + rp) and proj.is_contiguous() and xc.is_contiguous()
+    # the C entry point takes proj as `const float*` and encodes its TMA maps as FLOAT32: anything else (an fp16 /
+    # bf16 proj produced under autocast) would be read past its end
+    if proj.dtype != torch.float32:
+        raise TypeError(f"ss2d_core: proj must be float32, got {proj.dtype} (compute x_proj with autocast disabled)")
+    if xc.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"ss2d_core: xc must be float32 or bfloat16, got {xc.dtype}")
+    for name, t in (("Wdt", Wdt), ("dt_bias", dt_bias), ("A", A), ("Ds", Ds)):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"ss2d_core: {name} must be a contiguous float32 tensor")
+    if tuple(proj.shape) != (B, H, W, 4, 32 + rp) or not proj.is_contiguous() or not xc.is_contiguous():
+        raise ValueError(f"ss2d_core: proj must be a contiguous (B, H, W, 4, {32 + rp}) tensor and xc contiguous")
     ydir = torch.empty((B, H, W, 4, D), dtype=torch.float32, device=dev)
     hsave = (torch.empty((B, 4, core_train_blocks(H, W), D, 16), dtype=torch.float32, device=dev)
              if save_states else None)
@@ -285,6 +306,8 @@ def pack_x_proj(x_proj_weight: torch.Tensor, d_state: int, dt_rank: int) -> torc
     Built with differentiable torch ops, so autograd carries the gradient back to x_proj_weight."""
     K, _, D = x_proj_weight.shape
     R, N, rp = dt_rank, d_state, dt_pad(dt_rank)
+    if N > 16:
+        raise ValueError(f"d_state {N} > 16 is not supported by the fused SS2D kernel")
     w_dt, w_B, w_C = torch.split(x_proj_weight, [R, N, N], dim=1)
     pad = lambda t, n: F.pad(t, (0, 0, 0, n - t.shape[1]))
     return torch.cat((pad(w_B, 16), pad(w_C, 16), pad(w_dt, rp)), dim=1).reshape(K * (32 + rp), D)
@@ -305,7 +328,8 @@ def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias
         proj = torch.mm(xc.view(-1, D), w_packed.to(torch.bfloat16).t(), out_dtype=torch.float32).view(B, H, W, 4, -1)
     else:
         xc = dwconv3x3_silu(x, conv_w, conv_b)
-        proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+        with torch.autocast("cuda", enabled=False):      # fp32 x_proj whatever the caller's autocast dtype is
+            proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
     A = -torch.exp(A_logs.float())
     ydir = ss2d_core(xc, proj, dt_projs_weight.float().contiguous(), dt_projs_bias.float().contiguous(),
                      A.contiguous(), Ds.float().contiguous(), d_state, dt_rank)

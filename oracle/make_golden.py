@@ -127,10 +127,31 @@ def vssm_t_config1(mod, ref_scan):
                     first_x_proj=sd["layers.0.blocks.0.self_attention.x_proj_weight"]))
 
 
+def vssm_t_batch256(mod, ref_scan, n=256, chunk=8):
+    """The same MedMamba-T (seed 0 weights) on 256 randn images (seed 2), fp32, eval, in chunks of 8 (per-image
+    results do not depend on the chunking: eval-mode BatchNorm).  Reference logits for the bf16 top-1 check at one
+    full 256-image batch (BASELINE configs[2] lower batch bound)."""
+    mod.selective_scan_fn = ref_scan
+    torch.manual_seed(0)
+    net = mod.VSSM(depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], num_classes=6).eval()
+    torch.manual_seed(2)
+    x = torch.randn(n, 3, 224, 224)
+    outs = []
+    with torch.no_grad():
+        for i in range(0, n, chunk):
+            outs.append(net(x[i:i + chunk]))
+            print(f"  b256: {i + chunk}/{n}", flush=True)
+    return _np(dict(logits=torch.cat(outs), weight_seed=0, input_seed=2))
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     mod, iface = refload.load_reference()
     ref_scan = iface.selective_scan_ref
+    if "--b256" in sys.argv:          # ~6 minutes of CPU; kept apart from the quick fixtures
+        np.savez_compressed(os.path.join(OUT, "vssm_t_b256.npz"), **vssm_t_batch256(mod, ref_scan))
+        return
     np.savez_compressed(os.path.join(OUT, "scan_small.npz"), **scan_cases(ref_scan))
     np.savez_compressed(os.path.join(OUT, "index_maps.npz"), **index_cases(mod))
     np.savez_compressed(os.path.join(OUT, "ss2d_small.npz"), **ss2d_case(mod, ref_scan))

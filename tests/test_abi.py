@@ -25,7 +25,10 @@ def test_header_symbols_exported():
 def test_host_only_entry_points():
     from medmamba_b200 import _lib
     h = _lib.lib()
-    assert h.mmb_abi_version() == 1
+    assert h.mmb_abi_version() == _lib.ABI_VERSION == 2
+    h.mmb_source_digest.restype = ctypes.c_char_p
+    from medmamba_b200 import build
+    assert h.mmb_source_digest().decode() == build._digest()
     assert h.mmb_status_string(ctypes.c_int(0)) == b"ok"
     assert b"invalid" in h.mmb_status_string(ctypes.c_int(-1))
     assert [h.mmb_ss2d_core_dt_pad(ctypes.c_int(r)) for r in (3, 6, 12, 24, 32)] == [4, 8, 12, 24, 32]

@@ -100,9 +100,11 @@ def test_scan_fwd_empty_and_errors():
                           torch.zeros(1, 4, 16, 5))
 
 
+@pytest.mark.parametrize("batch", [4, 64])
 @pytest.mark.parametrize("KD,L", STAGE_SHAPES)
-def test_scan_fwd_bf16_io(KD, L):
-    inp = make_scan_inputs("stress", 4, KD, L, seed=L)
+def test_scan_fwd_bf16_io(KD, L, batch):
+    """BASELINE config 2 in bf16 I/O (state fp32), at the config's own batch of 64 and at a small one."""
+    inp = make_scan_inputs("stress", batch, KD, L, seed=L)
     q = lambda t: t.bfloat16().float()
     inp_q = dict(inp, u=q(inp["u"]), delta=q(inp["delta"]))
     out = _run(inp_q, dtype=torch.bfloat16)

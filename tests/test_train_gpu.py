@@ -100,6 +100,71 @@ def test_fused_backward_matches_interface_backward(d_model, H, W, B):
         assert err < 2e-3, f"{name}: fused vs interface backward differ by {err:.2e}"
 
 
+def _core_problem(B, H, W, D, R, seed, N=16):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    rp = {1: 4, 2: 4, 3: 4, 6: 8, 12: 12, 24: 24}[R]
+    xc = 0.3 * rn(B, H, W, D)
+    proj = 0.2 * rn(B, H, W, 4, 32 + rp)
+    proj[..., 32 + R:] = 0
+    Wdt = rn(4, D, R) * R ** -0.5
+    bias = rn(4, D) - 3.0
+    A = -torch.exp(0.3 * rn(4 * D, N)) * torch.arange(1, N + 1)
+    Ds = rn(4 * D)
+    dy = rn(B, H, W, D)
+    return xc, proj, Wdt, bias, A.contiguous(), Ds, dy
+
+
+@pytest.mark.parametrize("xc_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,D,R", [(2, 56, 56, 96, 3), (2, 28, 28, 192, 6), (4, 14, 14, 384, 12), (4, 7, 7, 768, 24),
+                                        (1, 9, 5, 40, 3), (3, 33, 6, 24, 2)])
+def test_core_bwd_vs_analytic_fp64_oracle(B, H, W, D, R, xc_dtype):
+    """mmb_ss2d_core_bwd DIRECTLY against the analytic fp64 backward of the scan (oracle/scan_ref.c, SURVEY.md
+    Appendix B) composed with the cross-scan index maps of Appendix A -- at the four MedMamba-T stage shapes, not
+    through the repo's other backward kernel.  Every output within 5e-4 of its own max-norm."""
+    from oracle import cscan
+    from medmamba_b200 import ops
+    from medmamba_b200.fused_autograd import core_bwd
+    N = 16
+    xc, proj, Wdt, bias, A, Ds, dy = _core_problem(B, H, W, D, R, seed=H * W + D + R)
+    if xc_dtype != torch.float32:
+        xc = xc.to(xc_dtype).float()              # the oracle sees the values the kernel reads
+    L = H * W
+    src = torch.from_numpy(medmamba_ref.cross_scan_index(H, W))                       # (4, L): position read at step l
+    xt, pt, dyt = xc.view(B, L, D), proj.view(B, L, 4, -1), dy.view(B, L, D)
+    u = torch.stack([xt[:, src[k]].transpose(1, 2) for k in range(4)], 1).reshape(B, 4 * D, L)
+    dout = torch.stack([dyt[:, src[k]].transpose(1, 2) for k in range(4)], 1).reshape(B, 4 * D, L)
+    dtr = [pt[:, src[k], k, 32:32 + R] for k in range(4)]                            # (B, L, R) per direction
+    draw = torch.stack([torch.einsum("blr,dr->bdl", dtr[k], Wdt[k]) for k in range(4)], 1).reshape(B, 4 * D, L)
+    Bm = torch.stack([pt[:, src[k], k, 0:N].transpose(1, 2) for k in range(4)], 1)   # (B, 4, N, L)
+    Cm = torch.stack([pt[:, src[k], k, 16:16 + N].transpose(1, 2) for k in range(4)], 1)
+    want = cscan.scan_bwd(u.contiguous(), draw.contiguous(), A, Bm.contiguous(), Cm.contiguous(), Ds, None,
+                          bias.reshape(-1), True, dout.contiguous())
+    w_dudir = torch.zeros(B, L, 4, D, dtype=torch.float64)
+    w_dproj = torch.zeros(B, L, 4, proj.shape[-1], dtype=torch.float64)
+    w_dW = torch.zeros(4, D, R, dtype=torch.float64)
+    for k in range(4):
+        du_k = want["du"][:, k * D:(k + 1) * D]                                        # (B, D, L) in time order
+        dd_k = want["ddelta"][:, k * D:(k + 1) * D]
+        w_dudir[:, src[k], k] = du_k.transpose(1, 2)
+        w_dproj[:, src[k], k, 0:N] = want["dB"][:, k].transpose(1, 2)
+        w_dproj[:, src[k], k, 16:16 + N] = want["dC"][:, k].transpose(1, 2)
+        w_dproj[:, src[k], k, 32:32 + R] = torch.einsum("bdl,dr->blr", dd_k, Wdt[k].double())
+        w_dW[k] = torch.einsum("bdl,blr->dr", dd_k, dtr[k].double())
+    c = lambda t: t.cuda().contiguous()
+    xg = c(xc).to(xc_dtype)
+    _, hsave = ops.ss2d_core(xg, c(proj), c(Wdt), c(bias), c(A), c(Ds), N, R, save_states=True)
+    dudir, dproj, dA, dW, dD, db = core_bwd(xg, c(proj), c(dy), c(Wdt), c(bias), c(A), c(Ds), hsave, N, R)
+    torch.cuda.synchronize()
+    checks = [("dudir", dudir.view(B, L, 4, D), w_dudir), ("dproj", dproj.view(B, L, 4, -1), w_dproj),
+              ("dA", dA, want["dA"]), ("dWdt", dW, w_dW), ("dDs", dD, want["dD"]),
+              ("d dt_bias", db.reshape(-1), want["ddelta_bias"])]
+    for name, got, ref in checks:
+        assert got.shape == ref.shape, name
+        err = (got.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        assert err < 5e-4, f"{name}: rel-to-max error {err:.2e}"
+
+
 @pytest.mark.parametrize("split", ["1", "2"])
 def test_fused_backward_both_lane_splits(split, monkeypatch):
     """The backward kernel's one- and two-lanes-per-channel instantiations agree with the interface backward."""
