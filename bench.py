@@ -2,28 +2,36 @@
 """bench.py -- MedMamba-T images/s at 224x224 on N B200 GPUs (BASELINE.json metric), one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype f32|bf16]
+                    [--workload infer|train] [--res R] [--no-extras] [--no-cpu-baseline]
 
-Own arm (default).  A step is one forward pass of MedMamba-T (depths [2,2,4,2], dims
-[96,192,384,768], 6 classes, random-init weights, eval mode) over one synthetic batch of B images
-per GPU -- the batch-sharded inference workload of BASELINE configs[2].  Every SS2D block runs the
-hand-written sm_100a kernels (dwconv+SiLU, the 4-direction TMA scan, out_norm*SiLU(z), shuffle +
-residual) through the C ABI; linears and the CNN branch are torch (cuBLAS / cuDNN).
-  value   : images/s with the input batch resident in HBM, K steps between CUDA events, max over ranks
-  e2e     : the same through the public host-facing call (medmamba_b200.InferencePipeline) with HOST (pinned)
-            images: every step's H2D copy + forward + logits D2H inside the timed region, the copy of the next
-            batch overlapped with the forward of the current one
-  roofline: the dominant kernel (ss2d_core_fwd at the stage-1 shape, L = 3136) timed live with CUDA
-            events on its launch stream inside the timed steps; algorithmic bytes are the fused
-            SS2D-core figure es*B*L*(2D + K(R+2N)) of SURVEY.md section 8(d).  The kernel is bound by
-            the MUFU exp rate (16/clk/SM), so the HBM fraction is small by construction; the
-            fraction of the exp ceiling is reported beside it as "alu".
-  cpu_baseline: the oracle port of the reference's CPU path (oracle.medmamba_ref.vssm_forward +
-            selective_scan_ref) on the host cores, bounded sample, rank 0 at N = 1 only.
-Multi-GPU (torchrun): one replica per GPU, independent batches, no data-path collective ("weak").
+Own arm (default).  A step is one forward pass of MedMamba-T (depths [2,2,4,2], dims [96,192,384,768], 6 classes,
+random-init weights, eval mode) over one synthetic batch of B images per GPU -- the batch-sharded inference workload
+of BASELINE configs[2].  Every SS2D block runs the hand-written sm_100a kernels (dwconv+SiLU, the 4-direction TMA
+scan, out_norm*SiLU(z), shuffle + residual) through the C ABI; linears and the CNN branch are torch (cuBLAS / cuDNN).
+  value    : images/s with the input batch resident in HBM, K steps between CUDA events, max over ranks
+  e2e      : the same through the public host-facing call (medmamba_b200.InferencePipeline) with HOST (pinned) images:
+             every step's H2D copy + forward + logits D2H inside the timed region, the copy of the next batch
+             overlapped with the forward of the current one
+  roofline : the dominant kernel (ss2d_core_fwd at the stage-1 shape) timed live with CUDA events on its launch
+             stream inside the timed steps.  Algorithmic bytes (fused SS2D-core figure with
+             per-tensor element sizes): B*L*(D*es_xc + D*es_y + 4*K*(R+2N)) -- xc read once, the merged y written
+             once, proj read once.  The kernel is bound by the MUFU exp rate (16/clk/SM), so the HBM fraction is
+             small by construction; the fraction of the exp ceiling is reported beside it as "alu".
+  roofline_stages : the same two fractions for all four MedMamba-T stage shapes of this run.
+  train    : BASELINE configs[3] as a sub-record -- a short data-parallel training step (CE + AdamW, batch 128 per GPU,
+             bf16 autocast) with the NCCL gradient all-reduce launched from gradient hooks during backward, timed after
+             the inference region; "allreduce_exposed_ms" is the step time with the exchange minus the step time
+             without it (N > 1).
+  configs  : BASELINE configs[0] (fp32, batch 8), configs[1] (isolated selective_scan_fn at the four stage shapes,
+             batch 64, fp32 and bf16, forward and forward+backward) and configs[4] (512x512, batch 32) as sub-records.
+  cpu_baseline: the oracle port of the reference's CPU path (oracle.medmamba_ref.vssm_forward + selective_scan_ref)
+             on the host cores, bounded sample, rank 0 at N = 1 only.
+Multi-GPU (torchrun): one replica per GPU, independent batches, no data-path collective ("weak"); the training
+sub-record is the one place with an exchange step.
 
-Reference arm (--impl reference): the reference's own CPU implementation of the path (the oracle
-port -- the reference is pure Python and /root/reference does not exist on the GPU box) timed on the
-host cores for the same metric; rank 0 only.
+Reference arm (--impl reference): the reference's own CPU implementation of the path (the oracle port -- the reference
+is pure Python and /root/reference does not exist on the GPU box) timed on the host cores for the same metric, 8 images
+per step; rank 0 only.
 """
 from __future__ import annotations
 
@@ -43,7 +51,9 @@ import torch  # noqa: E402
 METRIC = "MedMamba-T images/sec at 224x224"
 UNIT = "images/s"
 DEPTHS, DIMS, NUM_CLASSES, RES = [2, 2, 4, 2], [96, 192, 384, 768], 6, 224
+N_STATE, K_DIR = 16, 4
 MUFU_EXP_PER_S = 16 * 148 * 1.965e9          # MUFU.EX2 ceiling, measured (profiles/README.md)
+STAGE_SHAPES = [(384, 3136), (768, 784), (1536, 196), (3072, 49)]      # (K*D, L) of BASELINE configs[1]
 
 
 def measured_peaks():
@@ -134,15 +144,20 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_rate(budget_s: float, steps: int, warmup: int, seed: int = 0):
-    """images/s of the oracle port of the reference's CPU path.  Returns (value, per-step images, ms_per_step, cores)."""
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(images_per_step: int, steps: int, warmup: int, seed: int = 0, budget_s: float = 600.0):
+    """images/s of the oracle port of the reference's CPU path.  Returns (value, per-step images, ms_per_step, cores).
+    `images_per_step` is kept unless the whole run would exceed `budget_s` (then it is cut down and reported)."""
     import medmamba_b200 as mm
     from oracle import medmamba_ref
     # every host core: torchrun exports OMP_NUM_THREADS=1, which would leave the CPU arm on a single thread
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncpu = os.cpu_count() or 1
+    ncpu = host_cores()
     if torch.get_num_threads() < ncpu:
         torch.set_num_threads(ncpu)
     torch.manual_seed(seed)
@@ -150,10 +165,11 @@ def cpu_reference_rate(budget_s: float, steps: int, warmup: int, seed: int = 0):
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         x1 = torch.randn(1, 3, RES, RES, generator=g)
+        medmamba_ref.vssm_forward(sd, x1, depths=tuple(DEPTHS))          # untimed: thread pools, oneDNN primitives
         t0 = time.perf_counter()
         medmamba_ref.vssm_forward(sd, x1, depths=tuple(DEPTHS))
         t_img = time.perf_counter() - t0
-        nb = int(max(1, min(8, budget_s / ((steps + warmup) * t_img))))
+        nb = int(max(1, min(images_per_step, budget_s / ((steps + warmup) * t_img))))
         x = torch.randn(nb, 3, RES, RES, generator=g)
         for _ in range(warmup):
             medmamba_ref.vssm_forward(sd, x, depths=tuple(DEPTHS))
@@ -169,8 +185,9 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    value, nb, ms, cores = cpu_reference_rate(150.0, steps, warmup)
-    sample = f"{nb} images/step x {steps} steps (+{warmup} warm-up), fp32, oracle port of MedMamba.py + selective_scan_ref"
+    value, nb, ms, cores = cpu_reference_rate(8, steps, warmup)
+    sample = (f"{nb} images/step x {steps} steps (+{warmup} warm-up), fp32, oracle port of MedMamba.py + "
+              f"selective_scan_ref")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
@@ -183,8 +200,218 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if args.workload == "train":
+        return (f"MedMamba-T (depths {DEPTHS}, dims {DIMS}) training step (CE + AdamW), batch {args.batch}/GPU, "
+                f"{RES}x{RES}x3 synthetic, {NUM_CLASSES} classes (BASELINE configs[3])")
+    which = "BASELINE configs[4]" if RES == 512 else ("BASELINE configs[0] shape" if args.dtype == "f32" and args.batch == 8
+                                                      else "BASELINE configs[2] shape" if RES == 224 else "off-baseline shape")
     return (f"MedMamba-T (depths {DEPTHS}, dims {DIMS}) inference, batch {args.batch}/GPU, {RES}x{RES}x3 synthetic, "
-            f"{NUM_CLASSES} classes (BASELINE configs[2] shape)")
+            f"{NUM_CLASSES} classes ({which})")
+
+
+# --------------------------------------------------------------------------------------- rooflines
+def stage_table(res):
+    """(H, D, R) of the four MedMamba-T stages at image side `res`."""
+    out = []
+    for i, dim in enumerate(DIMS):
+        h = res // 4 // (2 ** i)
+        out.append((h, dim, -(-(dim // 2) // 16)))
+    return out
+
+
+def core_rooflines(kstats, B, res, dtype, peak):
+    """Per stage: algorithmic bytes / exps of one ss2d_core_fwd call over its CUDA-event duration."""
+    stages = []
+    es_x = 2 if dtype == "bf16" else 4                     # xc element size; proj is fp32
+    es_y = 4                                               # the merged y the reference produces is fp32 (MedMamba.py:280)
+    for si, (h, D, R) in enumerate(stage_table(res)):
+        L = h * h
+        key = next((k for k in kstats if k.startswith("ss2d_core_fwd[") and f"B={B},L={L},D={D}," in k), None)
+        if key is None:
+            continue
+        st = kstats[key]
+        sec = st["avg_ms"] * 1e-3
+        alg_bytes = B * L * (D * es_x + D * es_y + 4 * K_DIR * (R + 2 * N_STATE))
+        exps = B * K_DIR * D * L * N_STATE
+        stages.append({
+            "stage": si + 1, "kernel": key, "avg_ms": round(st["avg_ms"], 4), "launches": st["count"],
+            "algorithmic_bytes": alg_bytes, "achieved": round(alg_bytes / sec / 1e9, 1), "unit": "GB/s",
+            "frac": round(alg_bytes / sec / 1e9 / peak, 4),
+            "interface_equivalent_gbs": round(4 * B * L * (3 * K_DIR * D + 2 * K_DIR * N_STATE) / sec / 1e9, 1),
+            "alu": {"bound": "mufu_ex2", "achieved_gexp_s": round(exps / sec / 1e9, 1),
+                    "peak_gexp_s": round(MUFU_EXP_PER_S / 1e9, 1), "frac": round(exps / sec / MUFU_EXP_PER_S, 4)}})
+    return stages
+
+
+def timed_loop(fn, steps, dist=None):
+    """K calls of fn between CUDA events on the current stream, barrier + synchronize either side -> total ms."""
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), out
+
+
+def max_ms(values, dev, dist):
+    t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+# --------------------------------------------------------------------------------------- sub-records
+def infer_config_record(mm, ops, dev, dist, world, batch, res, dtype, steps, peak, label):
+    """A short inference measurement of another BASELINE config (fresh model, own warm-up), device-resident inputs."""
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    if dtype == "f32":
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        net = mm.medmamba_t(NUM_CLASSES).to(dev).eval()
+        x = torch.randn(batch, 3, res, res, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
+
+        def step():
+            with torch.no_grad(), amp:
+                return net(x)
+        for _ in range(3):
+            step()
+        timer = ops.KernelTimer()
+        ops.set_kernel_timer(timer)
+        ms, _ = timed_loop(step, steps, dist)
+        ops.set_kernel_timer(None)
+        ms = max_ms([ms], dev, dist)[0]
+        ks = timer.summary()
+        rec = {"workload": label, "dtype": dtype, "batch_per_gpu": batch, "res": res, "steps": steps,
+               "ms_per_step": round(ms / steps, 3), "value": round(world * batch * steps / (ms / 1e3), 1), "unit": UNIT,
+               "gpu_launches": timer.launches, "roofline_stages": core_rooflines(ks, batch, res, dtype, peak)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del net, x
+    torch.cuda.empty_cache()
+    return rec
+
+
+def scan_microbench_record(mm, dev, peak, batch=64, iters=10):
+    """BASELINE configs[1]: the drop-in selective_scan_fn alone at the four stage shapes, batch 64, fp32 and bf16 I/O,
+    forward and forward+backward; GB/s of the interface-level algorithmic bytes es*B*L*(3*KD + 2*K*N) (x3 with the
+    backward).  L2 is flushed between calls (a 256 MB write)."""
+    import math
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        for KD, L in STAGE_SHAPES:
+            g = torch.Generator(device=dev).manual_seed(KD + L)
+            rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+            u = (0.1 * rn(batch, KD, L)).to(dtype).requires_grad_()
+            delta = (0.03 * rn(batch, KD, L)).to(dtype).requires_grad_()
+            A = (-torch.arange(1, N_STATE + 1, device=dev, dtype=torch.float32)).repeat(KD, 1).requires_grad_()
+            Bm, Cm = (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_(), (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_()
+            D = torch.ones(KD, device=dev, requires_grad=True)
+            dt = torch.exp(torch.rand(KD, device=dev, generator=g) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
+            bias = (dt + torch.log(-torch.expm1(-dt))).requires_grad_()
+            dout = rn(batch, KD, L).to(dtype)
+            es = 2 if dtype == torch.bfloat16 else 4
+            fwd_bytes = batch * L * (es * 3 * KD + 4 * 2 * K_DIR * N_STATE)
+
+            def fwd():
+                with torch.no_grad():
+                    return mm.selective_scan_fn(u, delta, A, Bm, Cm, D, None, bias, True)
+
+            def fwd_bwd():
+                for t in (u, delta, A, Bm, Cm, D, bias):
+                    t.grad = None
+                mm.selective_scan_fn(u, delta, A, Bm, Cm, D, None, bias, True).backward(dout)
+
+            rec = {"dtype": name, "KD": KD, "L": L, "batch": batch}
+            for label, fn, nbytes in (("fwd", fwd, fwd_bytes), ("fwd_bwd", fwd_bwd, 3 * fwd_bytes)):
+                for _ in range(3):
+                    fn()
+                tot = 0.0
+                for _ in range(iters):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tot += e0.elapsed_time(e1)
+                ms = tot / iters
+                rec[label] = {"ms": round(ms, 4), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                              "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+            out.append(rec)
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf16"):
+    """BASELINE configs[3]: data-parallel training step (CE + AdamW, train.py:187-192, 277-288), batch per GPU, the
+    gradient average as NCCL all-reduces over flat buckets launched from gradient hooks during backward."""
+    torch.manual_seed(0)                                   # identical replicas
+    net = mm.medmamba_t(NUM_CLASSES).to(dev).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    red = mdist.GradAllReducer(net.parameters(), overlap=True)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(batch, 3, RES, RES, device=dev, generator=g)
+    y = torch.randint(0, NUM_CLASSES, (batch,), device=dev, generator=g)
+    amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
+    exchange = [True]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        red.begin_step()
+        with amp:
+            loss = torch.nn.functional.cross_entropy(net(x).float(), y)
+        if exchange[0]:
+            loss.backward()
+            red.finish()
+        else:                                   # the same step without the exchange (hooks see a finished bucket list)
+            red._works = [True] * len(red.buckets)
+            loss.backward()
+            red._works = [None] * len(red.buckets)
+            red._pending = [len(b) for b in red.buckets]
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    timer = ops.KernelTimer(timing=False)
+    ops.set_kernel_timer(timer)
+    ms, loss = timed_loop(step, steps, dist)
+    ops.set_kernel_timer(None)
+    fired = red.launched_in_backward
+    ms_noex = None
+    if world > 1:
+        exchange[0] = False
+        step()
+        ms_noex, _ = timed_loop(step, steps, dist)
+        exchange[0] = True
+    ms, ms_noex = max_ms([ms, ms_noex if ms_noex is not None else 0.0], dev, dist)
+    rec = {"workload": f"MedMamba-T training step (CE + AdamW), batch {batch}/GPU, {RES}x{RES} synthetic (BASELINE configs[3])",
+           "metric": "MedMamba-T training images/sec at 224x224", "dtype": dtype, "batch_per_gpu": batch,
+           "global_batch": world * batch, "steps": steps, "ms_per_step": round(ms / steps, 3),
+           "value": round(world * batch * steps / (ms / 1e3), 1), "unit": UNIT, "gpu_launches": timer.launches,
+           "parallelism": f"dp{world}, {len(red.buckets)} flat fp32 buckets ({sum(f.numel() for f in red.flat) * 4 / 1e6:.1f} MB), "
+                          f"NCCL all-reduce launched from gradient hooks during backward",
+           "allreduce": None if world == 1 else {
+               "buckets": len(red.buckets), "buckets_launched_during_backward": fired,
+               "ms_per_step_without_exchange": round(ms_noex / steps, 3),
+               "allreduce_exposed_ms": round((ms - ms_noex) / steps, 3),
+               "exposed_share_of_step": round((ms - ms_noex) / ms, 4)},
+           "loss": round(float(loss), 4)}
+    red.close()
+    del net, opt, red, x, y
+    torch.cuda.empty_cache()
+    return rec
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -199,7 +426,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     import medmamba_b200 as mm
-    from medmamba_b200 import ops
+    from medmamba_b200 import dist as mdist, ops
 
     torch.backends.cudnn.benchmark = True
     if args.dtype == "f32":
@@ -211,33 +438,21 @@ def run_ours(args):
     x = torch.randn(B, 3, RES, RES, device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
     amp = torch.autocast("cuda", dtype=torch.bfloat16) if args.dtype == "bf16" else torch.autocast("cuda", enabled=False)
 
-    def step(inp):
+    def step():
         with torch.no_grad(), amp:
-            return net(inp)
+            return net(x)
 
     for _ in range(max(3, args.warmup)):
-        out = step(x)
+        step()
     torch.cuda.synchronize()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- timed region: K steps, inputs resident in HBM -------------------------------------------
     timer = ops.KernelTimer()
     ops.set_kernel_timer(timer)
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step(x)
-    e1.record()
-    barrier()
+    ms_total, _ = timed_loop(step, args.steps, dist)
     ops.set_kernel_timer(None)
     clocks = sampler.stop() if sampler else None
-    ms_total = e0.elapsed_time(e1)
     launches = timer.launches
     kstats = timer.summary()
 
@@ -247,7 +462,9 @@ def run_ours(args):
     x_hosts = [torch.randn(B, 3, RES, RES).pin_memory() for _ in range(2)]
     for _ in pipe.stream(x_hosts):
         pass
-    barrier()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     n_out = 0
     for logits_host in pipe.stream(x_hosts[i & 1] for i in range(args.steps)):
@@ -255,12 +472,26 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert n_out == B * args.steps
-    x_host = x_hosts[0]
+    h2d_bytes = x_hosts[0].numel() * 4
+    ms_total, e2e_ms = max_ms([ms_total, e2e_s * 1e3], dev, dist)
+    del pipe, x_hosts, net, x
+    torch.cuda.empty_cache()
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = t.tolist()
+    peak, peak_src = measured_peaks()
+    extras = {}
+    if not args.no_extras:
+        tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+        extras["train"] = train_record(mm, ops, mdist, dev, dist, rank, world, 128, 5)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        cfgs = {}
+        cfgs["configs[0]"] = infer_config_record(mm, ops, dev, dist, world, 8, 224, "f32", 10, peak,
+                                                 "MedMamba-T fp32 forward, batch 8, 224x224 (BASELINE configs[0])")
+        cfgs["configs[4]"] = infer_config_record(mm, ops, dev, dist, world, 32, 512, "bf16", 5, peak,
+                                                 "MedMamba-T 512x512 inference, batch 32, stage-1 L = 16384 (BASELINE configs[4])")
+        if rank == 0 and world == 1:
+            cfgs["configs[1]"] = scan_microbench_record(mm, dev, peak)
+        extras["configs"] = cfgs
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -268,32 +499,23 @@ def run_ours(args):
 
     value = world * B * args.steps / (ms_total / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    peak, peak_src = measured_peaks()
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "core_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{args.dtype},{B}")
+        tj = json.load(open(tpath))
+        traffic = tj.get(f"{args.dtype},{B},{RES}", tj.get(f"{args.dtype},{B}") if RES == 224 else None)
+        traffic_src = tj.get("source", "ncu --set full capture of this command, committed under profiles/ (static: not re-measured by this run)")
+    stages = core_rooflines(kstats, B, RES, args.dtype, peak)
     roof = None
-    L1 = (RES // 4) ** 2
-    key = next((k for k in kstats if k.startswith("ss2d_core_fwd") and f"L={L1}," in k), None)
-    if key:
-        st = kstats[key]
-        D, R, N, K, L = 96, 3, 16, 4, L1
-        es_x = 2 if args.dtype == "bf16" else 4           # xc element size; proj and ydir are fp32
-        alg_bytes = B * L * (D * es_x + D * 4 + 4 * K * (R + 2 * N))
-        exps = B * K * D * L * N
-        ach = alg_bytes / (st["avg_ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": traffic, "kernel": key, "avg_ms": round(st["avg_ms"], 4), "launches": st["count"],
-                "peak_source": peak_src,
-                # what the reference-layout operator would have to move for the same work (interface level)
-                "interface_equivalent_gbs": round(4 * B * L * (3 * K * D + 2 * K * N) / (st["avg_ms"] * 1e-3) / 1e9, 1),
-                "alu": {"bound": "mufu_ex2", "achieved_gexp_s": round(exps / (st["avg_ms"] * 1e-3) / 1e9, 1),
-                        "peak_gexp_s": round(MUFU_EXP_PER_S / 1e9, 1),
-                        "frac": round(exps / (st["avg_ms"] * 1e-3) / MUFU_EXP_PER_S, 4)}}
+    if stages:
+        s1 = stages[0]
+        roof = {"bound": "hbm", "achieved": s1["achieved"], "peak": peak, "unit": "GB/s", "frac": s1["frac"],
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": s1["kernel"], "avg_ms": s1["avg_ms"],
+                "launches": s1["launches"], "peak_source": peak_src, "algorithmic_bytes": s1["algorithmic_bytes"],
+                "interface_equivalent_gbs": s1["interface_equivalent_gbs"], "alu": s1["alu"]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, nb, ms, cores = cpu_reference_rate(30.0, 2, 0)
+        v, nb, ms, cores = cpu_reference_rate(8, 2, 0, budget_s=40.0)
         cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 forwards of {nb} images, fp32, oracle port of MedMamba.py + selective_scan_ref ({2 * ms / 1e3:.1f} s)"}
     line = {
@@ -303,71 +525,40 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"batch-sharded replicas x{world}",
                    "l2": f"inputs ({B * 3 * RES * RES * 4 / 1e6:.0f} MB per step) and activations exceed the 126 MB L2; no flush needed",
                    "batch_sweep": "profiles/README.md (256 / 512 / 1024 per GPU)"},
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": B * NUM_CLASSES * 4},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_stages": stages, "cpu_baseline": cpu,
         "kernels": {k: {"avg_ms": round(v["avg_ms"], 4), "count": v["count"]} for k, v in sorted(kstats.items())},
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def run_train(args):
-    """BASELINE configs[3]: data-parallel training step (CE loss + AdamW, train.py:187-192), batch B per GPU,
-    gradients averaged with NCCL all-reduces over flat buckets.  One JSON line, same contract."""
+    """BASELINE configs[3] as the whole run (`--workload train`): one JSON line, same contract."""
     rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import medmamba_b200 as mm
     from medmamba_b200 import dist as mdist, ops
     mdist.init_from_env("nccl")
+    dist = torch.distributed if world > 1 else None
     torch.backends.cudnn.benchmark = True
-    torch.manual_seed(0)                                   # identical replicas
-    net = mm.medmamba_t(NUM_CLASSES).to(dev).train()
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
-    red = mdist.GradAllReducer(net.parameters())
-    B = args.batch
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
-    x = torch.randn(B, 3, RES, RES, device=dev, generator=g)
-    y = torch.randint(0, NUM_CLASSES, (B,), device=dev, generator=g)
-    amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        with amp:
-            loss = torch.nn.functional.cross_entropy(net(x).float(), y)
-        loss.backward()
-        red.reduce()
-        opt.step()
-        return loss
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    timer = ops.KernelTimer(timing=False)
-    ops.set_kernel_timer(timer)
     sampler = ClockSampler(local) if rank == 0 else None
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ops.set_kernel_timer(None)
+    rec = train_record(mm, ops, mdist, dev, dist, rank, world, args.batch, args.steps, args.dtype)
     clocks = sampler.stop() if sampler else None
-    ms = mdist.max_over_ranks([e0.elapsed_time(e1)], device=dev)[0]
     if rank == 0:
         print(json.dumps({
-            "metric": "MedMamba-T training images/sec at 224x224", "value": round(world * B * args.steps / (ms / 1e3), 1),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"MedMamba-T training step (CE + AdamW), batch {B}/GPU, {RES}x{RES} synthetic (BASELINE configs[3])",
-                       "global_batch": world * B, "parallelism": f"dp{world}, flat-bucket NCCL all-reduce"},
-            "gpu_launches": timer.launches, "clocks": clocks, "loss": round(float(loss), 4)}), flush=True)
+            "metric": rec["metric"], "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": 3, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": rec["workload"], "global_batch": rec["global_batch"], "parallelism": rec["parallelism"]},
+            "gpu_launches": rec["gpu_launches"], "clocks": clocks, "allreduce": rec["allreduce"], "loss": rec["loss"]}),
+            flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -378,12 +569,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step (BASELINE configs[2]: 256-1024)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 1024 for inference: the "
+                    "top of BASELINE configs[2]'s 256-1024 range; 128 for --workload train)")
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the train / configs sub-records")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"])
     ap.add_argument("--res", type=int, default=224, help="image side; 512 with --batch 32 is BASELINE configs[4]")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 128 if args.workload == "train" else 1024
     global RES
     RES = args.res
     if args.impl == "reference":

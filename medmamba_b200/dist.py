@@ -51,11 +51,18 @@ def max_over_ranks(values: Iterable[float], device=None) -> List[float]:
 class GradAllReducer:
     """Average gradients over ranks through flat fp32 buckets (one all-reduce per bucket).
 
-    Buckets are laid out once in reverse parameter order (the order backward produces gradients in);
-    ``reduce()`` packs, all-reduces asynchronously, unpacks and scales by 1/world.  Parameters without a
-    gradient contribute zeros so every rank issues identical collectives."""
+    Buckets are laid out once in reverse parameter order (the order backward produces gradients in).
+    Two ways to drive it:
 
-    def __init__(self, params, bucket_mb: float = 32.0):
+    * ``reduce()`` after ``loss.backward()``: packs, all-reduces asynchronously, unpacks and scales by 1/world.
+    * ``overlap=True``: a post-accumulate hook on every parameter counts the gradients of its bucket; the bucket is
+      packed and its all-reduce launched the moment its last gradient is final, so the exchange of the late layers
+      travels over NVLink while backward is still computing the early ones (train.py:284 has no counterpart: the
+      reference is single-GPU).  ``finish()`` before ``optimizer.step()`` launches whatever did not fire (parameters
+      without a gradient contribute zeros so every rank issues identical collectives), waits and unpacks.
+    """
+
+    def __init__(self, params, bucket_mb: float = 32.0, overlap: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         cap = int(bucket_mb * (1 << 20) // 4)
@@ -77,25 +84,72 @@ class GradAllReducer:
                 vs.append(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
             self.views.append(vs)
+        self.overlap = bool(overlap) and self.world > 1
+        self._works = [None] * len(self.buckets)
+        self._pending = [len(b) for b in self.buckets]
+        self._hooks = []
+        self.launched_in_backward = 0                       # buckets whose all-reduce started from a hook (last step)
+        if self.overlap:
+            for bi, bucket in enumerate(self.buckets):
+                for p in bucket:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _make_hook(self, bi: int):
+        def hook(_param):
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0 and self._works[bi] is None:
+                self._launch(bi)
+                self.launched_in_backward += 1
+        return hook
+
+    def _launch(self, bi: int) -> None:
+        bucket, flat, views = self.buckets[bi], self.flat[bi], self.views[bi]
+        missing = [v for p, v in zip(bucket, views) if p.grad is None]
+        if missing:
+            torch._foreach_zero_(missing)
+        have = [(v, p.grad) for p, v in zip(bucket, views) if p.grad is not None]
+        if have:
+            # one multi-tensor kernel per bucket instead of one copy per parameter (~300 parameters)
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+
+    def _unpack(self, bi: int) -> None:
+        bucket, flat, views = self.buckets[bi], self.flat[bi], self.views[bi]
+        self._works[bi].wait()
+        flat.mul_(1.0 / self.world)
+        for p, v in zip(bucket, views):
+            if p.grad is None:
+                p.grad = v.to(p.dtype).clone()
+        torch._foreach_copy_([p.grad for p in bucket], views)
+
+    def finish(self) -> None:
+        """Overlapped mode: launch the buckets no hook completed, wait for all of them, write the averages back."""
+        if self.world == 1:
+            return
+        for bi in range(len(self.buckets)):
+            if self._works[bi] is None:
+                self._launch(bi)
+        for bi in range(len(self.buckets)):
+            self._unpack(bi)
+        self._works = [None] * len(self.buckets)
+        self._pending = [len(b) for b in self.buckets]
+
+    def begin_step(self) -> None:
+        """Overlapped mode: call before backward (resets the per-step launch counter)."""
+        self.launched_in_backward = 0
 
     def reduce(self) -> None:
         if self.world == 1:
             return
-        works = []
-        for bucket, flat, views in zip(self.buckets, self.flat, self.views):
-            missing = [v for p, v in zip(bucket, views) if p.grad is None]
-            if missing:
-                torch._foreach_zero_(missing)
-            have = [(v, p.grad) for p, v in zip(bucket, views) if p.grad is not None]
-            if have:
-                # one multi-tensor kernel per bucket instead of one copy per parameter (~300 parameters)
-                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
-        inv = 1.0 / self.world
-        for bucket, flat, views, w in zip(self.buckets, self.flat, self.views, works):
-            w.wait()
-            flat.mul_(inv)
-            for p, v in zip(bucket, views):
-                if p.grad is None:
-                    p.grad = v.to(p.dtype).clone()
-            torch._foreach_copy_([p.grad for p in bucket], views)
+        if self.overlap:
+            return self.finish()
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        for bi in range(len(self.buckets)):
+            self._unpack(bi)
+        self._works = [None] * len(self.buckets)
+
+    def close(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -41,7 +41,24 @@ def _worker(rank, world, port, q):
     torch.nn.functional.mse_loss(model(data), target).backward()
     want = [p.grad.clone() for p in model.parameters()]
     ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(got, want))
-    q.put((rank, sizes, mx, ok, len(red.buckets)))
+    # overlapped mode: all-reduces launched from gradient hooks during backward, two steps (state resets), and a
+    # parameter that takes no part in the loss (its bucket is completed by finish() with zeros)
+    model.zero_grad(set_to_none=True)
+    extra = torch.nn.Parameter(torch.ones(5))
+    red2 = mdist.GradAllReducer(list(model.parameters()) + [extra], bucket_mb=0.0001, overlap=True)
+    ok2, fired = True, 0
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        red2.begin_step()
+        torch.nn.functional.mse_loss(model(data[lo:hi]), target[lo:hi]).backward()
+        fired = red2.launched_in_backward
+        red2.finish()
+        got2 = [p.grad.clone() for p in model.parameters()]
+        ok2 = ok2 and all(torch.allclose(a, b, atol=1e-6) for a, b in zip(got2, want))
+        ok2 = ok2 and extra.grad is not None and float(extra.grad.abs().max()) == 0.0
+        extra.grad = None
+    red2.close()
+    q.put((rank, sizes, mx, ok and ok2, len(red.buckets), fired))
     dist.destroy_process_group()
 
 
@@ -56,11 +73,12 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, sizes, mx, ok, nb in res:
+    for rank, sizes, mx, ok, nb, fired in res:
         assert sizes == [(0, 6), (6, 11)]
         assert mx == [11.0, 5.0]
         assert ok, "bucketed gradient average differs from the global-batch gradient"
         assert nb > 1
+        assert fired >= 1, "no bucket was all-reduced from a gradient hook during backward"
 
 
 def test_shard_range_properties():
