@@ -32,7 +32,7 @@ extern "C" {
 
 typedef enum { MMB_F32 = 0, MMB_BF16 = 1, MMB_F16 = 2 } mmb_dtype;
 
-#define MMB_ABI_VERSION 2
+#define MMB_ABI_VERSION 3
 
 /* ABI version of the loaded library (host only, no CUDA call). */
 int mmb_abi_version(void);
@@ -122,7 +122,14 @@ int mmb_ss2d_core_train_blocks(int H, int W);
 int mmb_ss2d_core_plan(int batch, int H, int W, int D, int* lanes_per_channel, int* channels_per_cta,
                        int* channel_tiles);
 
-/* Four-direction selective scan of SS2D.forward_corev0 in one launch.  Replaces the cross-scan
+/* Workspace of mmb_ss2d_core_fwd for this problem, in bytes (host only, nothing is launched; < 0: status).  The
+ * caller allocates it (any contents; 16-byte aligned) and passes it to every forward call of that shape.  It holds the
+ * segment summaries of the L-parallel passes.  Optional outputs describe the plan: segments per sequence (1 = the
+ * sequences run whole, no workspace is touched) and resident CTAs per SM.  save_states != 0 plans the training forward. */
+int64_t mmb_ss2d_core_fwd_workspace_bytes(int batch, int H, int W, int D, int dstate, int dt_rank, int xc_dtype,
+                                          int save_states, int* segments, int* ctas_per_sm);
+
+/* Four-direction selective scan of SS2D.forward_corev0 in one call.  Replaces the cross-scan
  * (MedMamba.py:256-257), the dt_proj einsum and its copy (:262, :266), selective_scan_fn (:273-279,
  * delta_softplus=True, delta_bias=dt_projs_bias, z=None) and the flips / transposes of the
  * cross-merge (:282-286).
@@ -130,24 +137,33 @@ int mmb_ss2d_core_plan(int batch, int H, int W, int D, int* lanes_per_channel, i
  *   proj  : (batch, H, W, 4, 32 + dt_pad) fp32 -- per direction k the x_proj of the token:
  *           [0,16) = B_n, [16,32) = C_n (rows n >= dstate zero), [32, 32+dt_rank) = dt_r, rest zero
  *   Wdt   : (4, D, dt_rank)   dt_bias: (4, D)   A: (4*D, dstate) (= -exp(A_logs))   Ds: (4*D)
- *   ydir  : (batch, H, W, 4, D) fp32 -- direction k's scan output stored at the token it belongs to
+ *   ydir  : (batch, H, W, 4, D) in ydir_dtype (MMB_F32, or MMB_BF16 with bf16 xc) -- direction k's scan output
+ *           stored at the token it belongs to.
+ *           MMB_F32: y_k = <C, h> + Ds_k * u.   MMB_BF16: the state term <C, h> alone (rounded to bf16);
+ *           mmb_outnorm_gate_fwd adds u * sum_k Ds_k in fp32, so the large skip term is never rounded to bf16.
  *   hsave : NULL (inference), or (batch, 4, mmb_ss2d_core_train_blocks(H, W), D, 16) fp32: the state after
  *           every block of 8 steps, in each direction's own time order -- what mmb_ss2d_core_bwd recomputes from
+ *   workspace : mmb_ss2d_core_fwd_workspace_bytes(...) bytes of scratch (see there)
+ * Launches with fewer sequences than resident CTA slots split every sequence into segments: a first pass computes
+ * the segment summaries (end state from a zero start, sum of delta), a second pass scans all segments in parallel
+ * from the carried prefixes (the chunked scan north_star asks for).  A, Wdt 16-byte aligned.
  * Direction order and index maps: SURVEY.md Appendix A.  D % 4 == 0 (fp32 xc) or D % 8 == 0 (bf16 xc),
  * dstate <= 16, dt_rank <= 32. */
 int mmb_ss2d_core_fwd(const void* xc, const float* proj, const float* Wdt, const float* dt_bias,
-                      const float* A, const float* Ds, float* ydir, float* hsave,
-                      int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad, int xc_dtype,
-                      void* stream);
+                      const float* A, const float* Ds, void* ydir, float* hsave, void* workspace,
+                      int64_t workspace_bytes, int batch, int H, int W, int D, int dstate, int dt_rank, int dt_pad,
+                      int xc_dtype, int ydir_dtype, void* stream);
 
 /* y = ((y0 + y2) + y1) + y3 over ydir's direction slices (the operand order of MedMamba.py:298),
  * LayerNorm over D (MedMamba.py:300, eps as given) and * SiLU(z) (MedMamba.py:301).
- *   ydir : (tokens, 4, D) fp32;  z: (tokens, D) view with pixel stride z_pixel_stride, dtype z_dtype
+ *   ydir : (tokens, 4, D), ydir_dtype MMB_F32 (full y_k) or MMB_BF16 (state terms only: then u = xc (tokens, D)
+ *          bf16 dense and Dsum (D) fp32 = sum_k Ds_k must be given and y += u * Dsum);
+ *   z    : (tokens, D) view with pixel stride z_pixel_stride, dtype z_dtype
  *   out  : (tokens, D) dense, dtype out_dtype (== z_dtype);  ymerged: NULL or (tokens, D) fp32, the
  *          pre-norm sum (kept for the backward).  D % 4 == 0, D <= 1024. */
-int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const float* gamma, const float* beta,
-                         void* out, float* ymerged, int64_t tokens, int D, int64_t z_pixel_stride,
-                         float eps, int z_dtype, int out_dtype, void* stream);
+int mmb_outnorm_gate_fwd(const void* ydir, const void* z, const float* gamma, const float* beta,
+                         void* out, float* ymerged, const void* xc, const float* Dsum, int64_t tokens, int D,
+                         int64_t z_pixel_stride, float eps, int ydir_dtype, int z_dtype, int out_dtype, void* stream);
 
 /* out[..., 2j] = left[..., j] + inp[..., 2j];  out[..., 2j+1] = ssm[..., j] + inp[..., 2j+1]
  * -- torch.cat + channel_shuffle(groups=2) + residual of MedMamba.py:355-357 (:308-320).

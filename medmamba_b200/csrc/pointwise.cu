@@ -3,6 +3,8 @@
 //   (y0+y2+y1+y3) -> LayerNorm -> * SiLU(z)   replaces MedMamba.py:298-301 (3 adds, transpose copy, LN, gate)
 //   cat + channel_shuffle(2) + residual       replaces MedMamba.py:355-357 and :308-320
 // Each reads its inputs once with 128-bit loads and writes its output once.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mmb {
@@ -186,26 +188,36 @@ dwconv3x3_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* _
 // One warp per token: y = ((y0 + y2) + y1) + y3 over the four direction slices of ydir (B, L, 4, D)
 // -- the order of `y1 + y2 + y3 + y4` at MedMamba.py:298, whose operands are out0, flipped out2,
 // transposed out1, flipped-transposed out3 (MedMamba.py:286) -- then LayerNorm over D and * SiLU(z).
-template <int V, typename z_t, typename out_t>   // V float4 per lane: D <= 128 * V
+// y_t = float: the slices hold y_k = <C, h> + D_k u.  y_t = bf16 (autocast path): the slices hold the state terms only
+// and the skip term u * sum_k D_k is added here in fp32 from xc.
+template <int V, typename z_t, typename out_t, typename y_t>   // V float4 per lane: D <= 128 * V
 __global__ void __launch_bounds__(256)
-outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, const float* __restrict__ gamma,
+outnorm_gate_kernel(const y_t* __restrict__ ydir, const z_t* __restrict__ z, const float* __restrict__ gamma,
                     const float* __restrict__ beta, out_t* __restrict__ out, float* __restrict__ ymerged,
+                    const __nv_bfloat16* __restrict__ xc, const float* __restrict__ Dsum,
                     int64_t tokens, int D, int64_t z_pix, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int C4 = D / 4;
     for (int64_t tok = warp; tok < tokens; tok += nwarps) {
-        const float4* y0 = reinterpret_cast<const float4*>(ydir + tok * 4 * D);
+        const y_t* y0 = ydir + tok * 4 * D;
         float4 v[V];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const int c4 = lane + 32 * i;
             if (c4 < C4) {
-                const float4 a = __ldg(y0 + c4), bq = __ldg(y0 + C4 + c4), cq = __ldg(y0 + 2 * C4 + c4), dq = __ldg(y0 + 3 * C4 + c4);
+                const float4 a = load4<y_t>(y0 + 4 * c4), bq = load4<y_t>(y0 + D + 4 * c4), cq = load4<y_t>(y0 + 2 * D + 4 * c4),
+                             dq = load4<y_t>(y0 + 3 * D + 4 * c4);
                 v[i].x = ((a.x + cq.x) + bq.x) + dq.x; v[i].y = ((a.y + cq.y) + bq.y) + dq.y;
                 v[i].z = ((a.z + cq.z) + bq.z) + dq.z; v[i].w = ((a.w + cq.w) + bq.w) + dq.w;
+                if constexpr (!std::is_same<y_t, float>::value) {
+                    const float4 u = load4<__nv_bfloat16>(xc + tok * D + 4 * c4);
+                    const float4 ds = __ldg(reinterpret_cast<const float4*>(Dsum) + c4);
+                    v[i].x = fmaf(u.x, ds.x, v[i].x); v[i].y = fmaf(u.y, ds.y, v[i].y);
+                    v[i].z = fmaf(u.z, ds.z, v[i].z); v[i].w = fmaf(u.w, ds.w, v[i].w);
+                }
                 sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
                 if (ymerged) reinterpret_cast<float4*>(ymerged + tok * D)[c4] = v[i];
             } else {
@@ -239,6 +251,118 @@ outnorm_gate_kernel(const float* __restrict__ ydir, const z_t* __restrict__ z, c
                 o.z = fmaf((v[i].z - mean) * rstd, g.z, bt.z) * silu_f(zz.z);
                 o.w = fmaf((v[i].w - mean) * rstd, g.w, bt.w) * silu_f(zz.w);
                 store4<out_t>(out + tok * D + 4 * c4, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The autocast layout of the same operation: bf16 direction slices holding the state terms, bf16 xc / z / out.
+// Eight channels (one 128-bit load) per lane and vector, G lanes per token so that narrow rows keep the lanes busy
+// (D = 96: 12 vectors -> 16-lane groups, two tokens per warp).  y = ((s0 + s2) + s1) + s3 + u * sum_k D_k in fp32.
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    F8 o;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y;
+    }
+    return o;
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const F8& a) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ F8 ld_f32x8(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    F8 o;
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+    return o;
+}
+
+template <int V, int G>
+__global__ void __launch_bounds__(256)
+outnorm_gate_bf16x8_kernel(const __nv_bfloat16* __restrict__ ydir, const __nv_bfloat16* __restrict__ z,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           __nv_bfloat16* __restrict__ out, float* __restrict__ ymerged,
+                           const __nv_bfloat16* __restrict__ xc, const float* __restrict__ Dsum,
+                           int64_t tokens, int D, int64_t z_pix, float eps) {
+    constexpr int TPW = 32 / G;
+    constexpr bool HOIST = V <= 2;                   // per-channel constants in registers for the whole token loop
+    const int lane = threadIdx.x & 31, gl = lane % G;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int C8 = D / 8;
+    const int64_t ngroups = (tokens + TPW - 1) / TPW;
+    F8 gm[HOIST ? V : 1], bt[HOIST ? V : 1], dsm[HOIST ? V : 1];
+    if (HOIST) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c8 = gl + G * i;
+            if (c8 < C8) { gm[i] = ld_f32x8(gamma + 8 * c8); bt[i] = ld_f32x8(beta + 8 * c8); dsm[i] = ld_f32x8(Dsum + 8 * c8); }
+        }
+    }
+    for (int64_t grp = warp; grp < ngroups; grp += nwarps) {
+        const int64_t tok = grp * TPW + lane / G;
+        const bool tvalid = tok < tokens;
+        const __nv_bfloat16* y0 = ydir + tok * 4 * D;
+        F8 v[V];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c8 = gl + G * i;
+            if (tvalid && c8 < C8) {
+                const F8 a = ld_bf16x8(y0 + 8 * c8), bq = ld_bf16x8(y0 + D + 8 * c8), cq = ld_bf16x8(y0 + 2 * D + 8 * c8),
+                         dq = ld_bf16x8(y0 + 3 * D + 8 * c8), u = ld_bf16x8(xc + tok * D + 8 * c8);
+                const F8 ds = HOIST ? dsm[i] : ld_f32x8(Dsum + 8 * c8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[i].v[e] = fmaf(u.v[e], ds.v[e], ((a.v[e] + cq.v[e]) + bq.v[e]) + dq.v[e]);
+                    sum += v[i].v[e];
+                }
+                if (ymerged) {
+                    float4* m = reinterpret_cast<float4*>(ymerged + tok * D + 8 * c8);
+                    m[0] = make_float4(v[i].v[0], v[i].v[1], v[i].v[2], v[i].v[3]);
+                    m[1] = make_float4(v[i].v[4], v[i].v[5], v[i].v[6], v[i].v[7]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[i].v[e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum / (float)D;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (gl + G * i < C8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[i].v[e] -= mean; sq = fmaf(v[i].v[e], v[i].v[e], sq); }
+            }
+        }
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        const float rstd = rsqrtf(sq / (float)D + eps);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c8 = gl + G * i;
+            if (tvalid && c8 < C8) {
+                const F8 g = HOIST ? gm[i] : ld_f32x8(gamma + 8 * c8);
+                const F8 b = HOIST ? bt[i] : ld_f32x8(beta + 8 * c8);
+                const F8 zz = ld_bf16x8(z + tok * z_pix + 8 * c8);
+                F8 o;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o.v[e] = fmaf(v[i].v[e] * rstd, g.v[e], b.v[e]) * silu_f(zz.v[e]);
+                st_bf16x8(out + tok * D + 8 * c8, o);
             }
         }
     }
@@ -423,35 +547,67 @@ extern "C" int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* 
     return MMB_ERR_UNSUPPORTED;
 }
 
-extern "C" int mmb_outnorm_gate_fwd(const float* ydir, const void* z, const float* gamma, const float* beta,
-                                    void* out, float* ymerged, int64_t tokens, int D, int64_t z_pixel_stride,
-                                    float eps, int z_dtype, int out_dtype, void* stream) {
+extern "C" int mmb_outnorm_gate_fwd(const void* ydir, const void* z, const float* gamma, const float* beta,
+                                    void* out, float* ymerged, const void* xc, const float* Dsum, int64_t tokens, int D,
+                                    int64_t z_pixel_stride, float eps, int ydir_dtype, int z_dtype, int out_dtype,
+                                    void* stream) {
     using namespace mmb;
     if (!ydir || !z || !gamma || !beta || !out) return MMB_ERR_INVALID_ARG;
     if (tokens < 0 || D <= 0) return MMB_ERR_INVALID_ARG;
     if (D % 4 != 0 || D > 1024 || z_pixel_stride % 4 != 0 || z_dtype != out_dtype) return MMB_ERR_UNSUPPORTED;
+    if (ydir_dtype != MMB_F32 && ydir_dtype != MMB_BF16) return MMB_ERR_UNSUPPORTED;
+    if (ydir_dtype == MMB_BF16 && (!xc || !Dsum)) return MMB_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(ydir) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
-         reinterpret_cast<uintptr_t>(ymerged)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
+         reinterpret_cast<uintptr_t>(ymerged) | reinterpret_cast<uintptr_t>(xc) | reinterpret_cast<uintptr_t>(Dsum)) % 16 != 0)
+        return MMB_ERR_UNSUPPORTED;
     if (tokens == 0) return MMB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (ydir_dtype == MMB_BF16 && z_dtype == MMB_BF16 && D % 8 == 0 && z_pixel_stride % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
+        auto yb = reinterpret_cast<const __nv_bfloat16*>(ydir);
+        auto zb = reinterpret_cast<const __nv_bfloat16*>(z);
+        auto xb = reinterpret_cast<const __nv_bfloat16*>(xc);
+        auto ob = reinterpret_cast<__nv_bfloat16*>(out);
+        const int C8 = D / 8;
+#define MMB_X8(V, G)                                                                                             \
+        do {                                                                                                     \
+            const int g8 = grid_for(tokens * G, 256);                                                            \
+            outnorm_gate_bf16x8_kernel<V, G><<<g8, 256, 0, st>>>(yb, zb, gamma, beta, ob, ymerged, xb, Dsum,     \
+                                                                tokens, D, z_pixel_stride, eps);                 \
+            return launch_status();                                                                              \
+        } while (0)
+        if (C8 <= 8) MMB_X8(1, 8);
+        if (C8 <= 16) MMB_X8(1, 16);
+        if (C8 <= 32) MMB_X8(1, 32);
+        if (C8 <= 64) MMB_X8(2, 32);
+        if (C8 <= 96) MMB_X8(3, 32);
+        MMB_X8(4, 32);
+#undef MMB_X8
+    }
     const int grid = grid_for(tokens * 32, 256);
-#define MMB_ON(V, T)                                                                                             \
+#define MMB_ON(V, T, Y)                                                                                          \
     do {                                                                                                         \
         if (!aligned_for4<T>(z) || !aligned_for4<T>(out)) return MMB_ERR_UNSUPPORTED;                            \
-        outnorm_gate_kernel<V, T, T><<<grid, 256, 0, st>>>(ydir, reinterpret_cast<const T*>(z), gamma, beta,     \
-            reinterpret_cast<T*>(out), ymerged, tokens, D, z_pixel_stride, eps);                                 \
+        outnorm_gate_kernel<V, T, T, Y><<<grid, 256, 0, st>>>(reinterpret_cast<const Y*>(ydir),                  \
+            reinterpret_cast<const T*>(z), gamma, beta, reinterpret_cast<T*>(out), ymerged,                     \
+            reinterpret_cast<const __nv_bfloat16*>(xc), Dsum, tokens, D, z_pixel_stride, eps);                   \
         return launch_status();                                                                                  \
     } while (0)
-#define MMB_ON_V(T)                                                                                              \
+#define MMB_ON_V(T, Y)                                                                                           \
     do {                                                                                                         \
-        if (D <= 128) MMB_ON(1, T);                                                                              \
-        if (D <= 256) MMB_ON(2, T);                                                                              \
-        if (D <= 512) MMB_ON(4, T);                                                                              \
-        MMB_ON(8, T);                                                                                            \
+        if (D <= 128) MMB_ON(1, T, Y);                                                                           \
+        if (D <= 256) MMB_ON(2, T, Y);                                                                           \
+        if (D <= 512) MMB_ON(4, T, Y);                                                                           \
+        MMB_ON(8, T, Y);                                                                                         \
     } while (0)
-    if (z_dtype == MMB_F32) MMB_ON_V(float);
-    if (z_dtype == MMB_BF16) MMB_ON_V(__nv_bfloat16);
-    if (z_dtype == MMB_F16) MMB_ON_V(__half);
+    if (ydir_dtype == MMB_F32) {
+        if (z_dtype == MMB_F32) MMB_ON_V(float, float);
+        if (z_dtype == MMB_BF16) MMB_ON_V(__nv_bfloat16, float);
+        if (z_dtype == MMB_F16) MMB_ON_V(__half, float);
+    } else {
+        if (z_dtype == MMB_F32) MMB_ON_V(float, __nv_bfloat16);
+        if (z_dtype == MMB_BF16) MMB_ON_V(__nv_bfloat16, __nv_bfloat16);
+    }
 #undef MMB_ON_V
 #undef MMB_ON
     return MMB_ERR_UNSUPPORTED;

@@ -82,7 +82,7 @@ class CoreNormGateFn(torch.autograd.Function):
         Wdt_c, b_c, A_c, D_c = (Wdt.float().contiguous(), dt_bias.float().contiguous(), A.float().contiguous(),
                                 Ds.float().contiguous())
         ydir, hsave = ops.ss2d_core(xc, proj, Wdt_c, b_c, A_c, D_c, d_state, dt_rank, save_states=True)
-        y, merged = ops.outnorm_gate(ydir, z, gamma, beta, eps, want_merged=True)
+        y, merged = ops.outnorm_gate(ydir, z, gamma, beta, eps, want_merged=True, xc=xc, Ds=D_c)
         ctx.save_for_backward(xc, proj, z, Wdt_c, b_c, A_c, D_c, gamma, beta, merged, hsave)
         ctx.meta = (eps, d_state, dt_rank, Wdt.dtype, dt_bias.dtype, A.dtype, Ds.dtype)
         return y

@@ -6,6 +6,7 @@ the contract of each entry point and DESIGN.md for the data layout.  CUDA only -
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -103,8 +104,51 @@ def core_train_blocks(H: int, W: int) -> int:
     return n
 
 
+_core_ws = {}
+
+
+def core_workspace(dev, B: int, H: int, W: int, D: int, d_state: int, dt_rank: int, xc_dtype, save_states: bool):
+    """Scratch buffer of mmb_ss2d_core_fwd for this problem shape (segment summaries of the L-parallel passes, hand-off
+    states of the balanced persistent schedule), cached per (device, stream, shape): calls on one stream are ordered,
+    so they can share it; its size comes from the library's own planner."""
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    knobs = tuple(sorted((k, v) for k, v in os.environ.items() if k.startswith("MMB_CORE_")))     # debug knobs change the plan
+    key = (dev.index, stream, B, H, W, D, d_state, dt_rank, xc_dtype, bool(save_states), knobs)
+    ws = _core_ws.get(key)
+    if ws is None:
+        fn = lib().mmb_ss2d_core_fwd_workspace_bytes
+        fn.restype = ctypes.c_int64
+        with torch.cuda.device(dev):
+            n = fn(_c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
+                   _c_int(_DT_CODE[xc_dtype]), _c_int(int(save_states)), None, None)
+        if n < 0:
+            check(int(n), "mmb_ss2d_core_fwd_workspace_bytes")
+        if len(_core_ws) > 64:
+            _core_ws.clear()
+        ws = _core_ws[key] = torch.empty(int(n), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def core_plan(B: int, H: int, W: int, D: int, d_state: int, dt_rank: int, xc_dtype=torch.float32, save_states=False,
+              device=None):
+    """(segments per sequence, resident CTAs per SM) the forward would use; segments > 1 = the two L-parallel passes."""
+    fn = lib().mmb_ss2d_core_fwd_workspace_bytes
+    fn.restype = ctypes.c_int64
+    seg, occ = _c_int(), _c_int()
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        n = fn(_c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank), _c_int(_DT_CODE[xc_dtype]),
+               _c_int(int(save_states)), ctypes.byref(seg), ctypes.byref(occ))
+    if n < 0:
+        check(int(n), "mmb_ss2d_core_fwd_workspace_bytes")
+    return seg.value, occ.value
+
+
+_DT_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
 def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int, save_states: bool = False):
-    """xc (B, H, W, D) fp32 or bf16, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) fp32."""
+    """xc (B, H, W, D) fp32 or bf16, proj (B, H, W, 4, 32+RP) fp32 -> ydir (B, H, W, 4, D) in xc.dtype:
+    fp32: the four directional outputs y_k; bf16: their state terms only (y_k - Ds_k * u), see outnorm_gate."""
     dev = require_cuda(xc, proj, Wdt, dt_bias, A, Ds)
     B, H, W, D = xc.shape
     rp = dt_pad(dt_rank)
@@ -119,19 +163,26 @@ def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int, save_st
             raise TypeError(f"ss2d_core: {name} must be a contiguous float32 tensor")
     if tuple(proj.shape) != (B, H, W, 4, 32 + rp) or not proj.is_contiguous() or not xc.is_contiguous():
         raise ValueError(f"ss2d_core: proj must be a contiguous (B, H, W, 4, {32 + rp}) tensor and xc contiguous")
-    ydir = torch.empty((B, H, W, 4, D), dtype=torch.float32, device=dev)
+    ydt = torch.float32 if os.environ.get("MMB_CORE_YF32", "0") == "1" else xc.dtype
+    ydir = torch.empty((B, H, W, 4, D), dtype=ydt, device=dev)
     hsave = (torch.empty((B, 4, core_train_blocks(H, W), D, 16), dtype=torch.float32, device=dev)
              if save_states else None)
+    if B == 0:
+        return (ydir, hsave) if save_states else ydir
+    ws = core_workspace(dev, B, H, W, D, d_state, dt_rank, xc.dtype, save_states)
     with torch.cuda.device(dev), timed_launch("ss2d_core_fwd", f"B={B},L={H * W},D={D},R={dt_rank}"):
         st = lib().mmb_ss2d_core_fwd(ptr(xc), ptr(proj), ptr(Wdt), ptr(dt_bias), ptr(A), ptr(Ds), ptr(ydir), ptr(hsave),
-                                     _c_int(B), _c_int(H), _c_int(W), _c_int(D), _c_int(d_state), _c_int(dt_rank),
-                                     _c_int(rp), _c_int(dtype_code(xc)), stream_ptr(dev))
+                                     ptr(ws), i64(ws.numel()), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
+                                     _c_int(d_state), _c_int(dt_rank), _c_int(rp), _c_int(dtype_code(xc)),
+                                     _c_int(dtype_code(ydir)), stream_ptr(dev))
     check(st, "mmb_ss2d_core_fwd")
     return (ydir, hsave) if save_states else ydir
 
 
-def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
-    """ydir (B, H, W, 4, D) fp32, z (B, H, W, D) view -> LayerNorm(sum of directions) * SiLU(z)."""
+def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False, xc=None, Ds=None):
+    """ydir (B, H, W, 4, D) -> LayerNorm(sum of directions) * SiLU(z) with z a (B, H, W, D) view.  fp32 ydir holds the
+    full directional outputs; bf16 ydir holds their state terms and needs ``xc`` (bf16) and ``Ds`` (4*D) for the skip
+    term u * sum_k Ds_k, added in fp32."""
     dev = require_cuda(ydir, z, gamma, beta)
     B, H, W, K, D = ydir.shape
     z, z_px, _ = _token_view(z)
@@ -139,10 +190,18 @@ def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False):
     merged = torch.empty((B, H, W, D), dtype=torch.float32, device=dev) if want_merged else None
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
+    dsum = None
+    if ydir.dtype == torch.bfloat16:
+        if xc is None or Ds is None or xc.dtype != torch.bfloat16 or not xc.is_contiguous():
+            raise ValueError("outnorm_gate: bf16 direction slices need the contiguous bf16 xc and Ds they were split from")
+        dsum = Ds.detach().float().view(4, D).sum(0).contiguous()
+    elif ydir.dtype != torch.float32:
+        raise TypeError(f"outnorm_gate: ydir must be float32 or bfloat16, got {ydir.dtype}")
     with torch.cuda.device(dev), timed_launch("outnorm_gate_fwd", f"B={B},L={H * W},D={D}"):
-        st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged), i64(B * H * W),
-                                        _c_int(D), i64(z_px), ctypes.c_float(eps), _c_int(dtype_code(z)),
-                                        _c_int(dtype_code(out)), stream_ptr(dev))
+        st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged),
+                                        ptr(xc if dsum is not None else None), ptr(dsum), i64(B * H * W),
+                                        _c_int(D), i64(z_px), ctypes.c_float(eps), _c_int(dtype_code(ydir)),
+                                        _c_int(dtype_code(z)), _c_int(dtype_code(out)), stream_ptr(dev))
     check(st, "mmb_outnorm_gate_fwd")
     return (out, merged) if want_merged else out
 
@@ -333,7 +392,7 @@ def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias
     A = -torch.exp(A_logs.float())
     ydir = ss2d_core(xc, proj, dt_projs_weight.float().contiguous(), dt_projs_bias.float().contiguous(),
                      A.contiguous(), Ds.float().contiguous(), d_state, dt_rank)
-    return outnorm_gate(ydir, z, norm_w, norm_b, eps)
+    return outnorm_gate(ydir, z, norm_w, norm_b, eps, xc=xc, Ds=Ds)
 
 
 def shuffle_cat_residual(left, ssm, inp):

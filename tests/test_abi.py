@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 def test_host_only_entry_points():
     from medmamba_b200 import _lib
     h = _lib.lib()
-    assert h.mmb_abi_version() == _lib.ABI_VERSION == 2
+    assert h.mmb_abi_version() == _lib.ABI_VERSION == 3
     h.mmb_source_digest.restype = ctypes.c_char_p
     from medmamba_b200 import build
     assert h.mmb_source_digest().decode() == build._digest()
@@ -34,7 +34,7 @@ def test_host_only_entry_points():
     assert [h.mmb_ss2d_core_dt_pad(ctypes.c_int(r)) for r in (3, 6, 12, 24, 32)] == [4, 8, 12, 24, 32]
     assert h.mmb_ss2d_core_dt_pad(ctypes.c_int(33)) == -2
     # null pointers are rejected with a status, nothing is launched
-    assert h.mmb_ss2d_core_fwd(*([None] * 7), *([ctypes.c_int(1)] * 7), None) == -1
+    assert h.mmb_ss2d_core_fwd(*([None] * 9), ctypes.c_int64(0), *([ctypes.c_int(1)] * 9), None) == -1
 
 
 def test_product_does_not_import_oracle():

@@ -116,6 +116,75 @@ def test_core_directions_vs_oracle(B, H, W, D, R, N, stress):
         assert_close((ydir[..., k, :].cpu() - uD) / scale, (want - uD) / scale, 1e-4, 1e-5, f"direction {k} minus u*D")
 
 
+@pytest.mark.parametrize("B,H,W,D,R,segs", [(2, 56, 56, 96, 3, 7), (1, 128, 128, 96, 3, 0), (3, 28, 28, 192, 6, 3), (2, 40, 9, 40, 3, 2),
+                                            (1, 9, 70, 24, 2, 5), (2, 14, 14, 384, 12, 2), (8, 56, 56, 96, 3, 0)])
+@pytest.mark.parametrize("xc_dtype", [torch.float32, torch.bfloat16])
+def test_core_l_parallel_passes_match_whole_sequences(B, H, W, D, R, segs, xc_dtype, monkeypatch):
+    """The L-parallel schedule (segment summaries, then all segments from their carried prefixes -- north_star's
+    chunked scan) against the same kernel walking whole sequences (MMB_CORE_SEGS=1), and against the fp64 oracle.
+    segs = 0 leaves the choice to the planner (these shapes must pick more than one segment on their own)."""
+    from medmamba_b200 import ops
+    N = 16
+    prm = _random_ss2d_params(D, R, N, seed=H + W + D, stress=True)
+    x = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(2)) * 0.5
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda().to(xc_dtype)
+    wp = ops.pack_x_proj(prm["x_proj_weight"].cuda(), N, R)
+    proj = (xc.float().view(-1, D) @ wp.t()).view(B, H, W, 4, -1)
+    args = (xc, proj, prm["dt_projs_weight"].cuda().contiguous(), prm["dt_projs_bias"].cuda().contiguous(),
+            (-torch.exp(prm["A_logs"])).cuda().contiguous(), prm["Ds"].cuda().contiguous(), N, R)
+    if segs:
+        monkeypatch.setenv("MMB_CORE_S", "1")       # forced cases: one lane per channel (the build the passes exist for)
+    monkeypatch.setenv("MMB_CORE_SEGS", "1")
+    assert ops.core_plan(B, H, W, D, N, R, xc_dtype)[0] == 1
+    whole = ops.ss2d_core(*args).float()
+    if segs:
+        monkeypatch.setenv("MMB_CORE_SEGS", str(segs))
+    else:
+        monkeypatch.delenv("MMB_CORE_SEGS")
+    used = ops.core_plan(B, H, W, D, N, R, xc_dtype)[0]
+    assert used > 1 and (segs == 0 or used == segs), used
+    split = ops.ss2d_core(*args).float()
+    torch.cuda.synchronize()
+    scale = max(1.0, whole.abs().max().item())
+    tol = 2e-5 if xc_dtype == torch.float32 else 2 ** -7        # bf16 slices: one rounding of the state term
+    assert (split - whole).abs().max().item() <= tol * scale, (split - whole).abs().max().item() / scale
+    if xc_dtype == torch.float32:
+        ys = medmamba_ref.ss2d_core(x, prm["x_proj_weight"], prm["dt_projs_weight"], prm["dt_projs_bias"], prm["A_logs"],
+                                    prm["Ds"], scan_fn=cscan_fn)
+        for k, ref_i in enumerate([0, 2, 1, 3]):
+            want = ys[ref_i].reshape(B, D, H, W).permute(0, 2, 3, 1)
+            assert_close(split[..., k, :].cpu() / scale, want / scale, 1e-4, 1e-5, f"L-parallel direction {k}")
+
+
+def test_core_bf16_slices_hold_the_state_term():
+    """bf16 xc (autocast layout): ydir[..., k, :] = y_k - Ds_k * u rounded to bf16; with the skip term added back in
+    fp32 it matches the fp64 oracle to bf16 accuracy OF THE STATE TERM (not of the much larger u * D)."""
+    from medmamba_b200 import ops
+    B, H, W, D, R, N = 2, 28, 28, 192, 6, 16
+    prm = _random_ss2d_params(D, R, N, seed=11, stress=True)
+    x = (torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(3)) * 0.5).bfloat16().float()
+    ys = medmamba_ref.ss2d_core(x, prm["x_proj_weight"], prm["dt_projs_weight"], prm["dt_projs_bias"], prm["A_logs"], prm["Ds"],
+                                scan_fn=cscan_fn)
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+    wp = ops.pack_x_proj(prm["x_proj_weight"].cuda(), N, R)
+    proj = (xc.float().view(-1, D) @ wp.t()).view(B, H, W, 4, -1)
+    ydir = ops.ss2d_core(xc, proj, prm["dt_projs_weight"].cuda().contiguous(), prm["dt_projs_bias"].cuda().contiguous(),
+                         (-torch.exp(prm["A_logs"])).cuda().contiguous(), prm["Ds"].cuda().contiguous(), N, R)
+    assert ydir.dtype == torch.bfloat16
+    for k, ref_i in enumerate([0, 2, 1, 3]):
+        uD = (x * prm["Ds"].view(4, D)[k].view(1, D, 1, 1)).permute(0, 2, 3, 1)
+        want = ys[ref_i].reshape(B, D, H, W).permute(0, 2, 3, 1) - uD                # the state term
+        err = (ydir[..., k, :].float().cpu() - want).abs().max().item() / want.abs().max().item()
+        assert err < 2 ** -7, f"direction {k}: {err:.2e}"
+    # and the out_norm kernel puts the skip term back in fp32
+    z = torch.randn(B, H, W, D, generator=torch.Generator().manual_seed(4)).cuda().bfloat16()
+    gamma, beta = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    _, merged = ops.outnorm_gate(ydir, z, gamma, beta, 1e-5, want_merged=True, xc=xc, Ds=prm["Ds"].cuda())
+    want = sum(ys).reshape(B, D, H, W).permute(0, 2, 3, 1)
+    err = (merged.cpu() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-3, err
+
+
 def test_outnorm_gate():
     from medmamba_b200 import ops
     for (B, H, W, D) in [(2, 3, 5, 8), (2, 14, 14, 384), (1, 7, 7, 768), (2, 9, 9, 96), (1, 2, 2, 1024)]:
@@ -403,13 +472,16 @@ def _permute_dirs(proj, Wdt, bias, A, Ds, perm, D):
 
 
 @pytest.mark.parametrize("B,H,W,D,R", [(64, 56, 56, 96, 3), (3, 40, 72, 192, 6), (2, 9, 31, 40, 3), (256, 14, 14, 384, 12)])
-def test_core_index_maps_bit_exact_under_transpose_and_flip(B, H, W, D, R):
+def test_core_index_maps_bit_exact_under_transpose_and_flip(B, H, W, D, R, monkeypatch):
     """Size-independent property at the full stage shapes: transposing the token grid turns
     the row-order directions into the column-order ones, reversing it turns forward into backward.  With the
     per-direction parameters permuted the same way, every direction runs the same sequence of operations on the
     same numbers, so the outputs must agree BIT FOR BIT at the mapped positions -- whatever block geometry,
     ring path (row boxes / column boxes) or group mode the kernel picks for either layout."""
     from medmamba_b200 import ops
+    # whole sequences: the L-parallel passes cut a sequence at block borders that differ between the two layouts, and
+    # their carried decay products exp(A * sum delta) round differently from the step-by-step products
+    monkeypatch.setenv("MMB_CORE_SEGS", "1")
     xc, proj, Wdt, bias, A, Ds, N = _core_inputs_gpu(B, H, W, D, R, seed=H * W + D)
     y = ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R)
     # transpose: (h, w) -> (w, h); directions 0 <-> 1, 2 <-> 3

@@ -13,7 +13,10 @@ ap.add_argument("--noflush", action="store_true")
 ap.add_argument("--variants", default="", help="comma list of values of the --env variable to sweep in-process")
 ap.add_argument("--env", default="MMB_CORE_CT", help="environment knob swept by --variants (read by the library per call)")
 ap.add_argument("--bf16", action="store_true", help="bf16 xc (the autocast layout)")
+ap.add_argument("--res", type=int, default=224, help="image side (512 = BASELINE configs[4] stage shapes)")
 args = ap.parse_args()
+if args.res != 224:
+    STAGES = [(args.res // 4 // 2 ** i,) * 2 + (d, r) for i, (d, r) in enumerate(((96, 3), (192, 6), (384, 12), (768, 24)))]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 cases = [(si, v) for si in range(len(STAGES)) for v in (args.variants.split(",") if args.variants else [None])]
 for si, variant in cases:
@@ -21,10 +24,15 @@ for si, variant in cases:
     if args.stage >= 0 and si != args.stage:
         continue
     if variant is not None:
-        if variant == "default":
-            os.environ.pop(args.env, None)
-        else:
-            os.environ[args.env] = variant
+        for k in [k for k in os.environ if k.startswith("MMB_CORE_")]:
+            os.environ.pop(k)
+        if variant != "default":
+            if "=" in variant:          # "K1=V1+K2=V2": several knobs at once
+                for kv in variant.split("+"):
+                    k, v = kv.split("=")
+                    os.environ[k] = v
+            else:
+                os.environ[args.env] = variant
     B, N = args.batch, 16
     g = torch.Generator(device="cuda").manual_seed(0)
     xc = 0.1 * torch.randn(B, H, W, D, device="cuda", generator=g)
@@ -56,7 +64,9 @@ for si, variant in cases:
     exps = B * 4 * D * H * W * 16
     fused_bytes = 4 * B * H * W * (2 * D + 4 * (R + 32))
     iface_bytes = 4 * B * H * W * (3 * 4 * D + 2 * 4 * 16)
-    print(json.dumps(dict(stage=si + 1, batch=B, ms=round(ms, 4), min_ms=round(ts[0], 4),
+    plan = ops.core_plan(B, H, W, D, N, R, xc.dtype)
+    print(json.dumps(dict(stage=si + 1, batch=B, L=H * W, dtype=str(xc.dtype)[6:], plan=dict(segs=plan[0], ctas_per_sm=plan[1]),
+                          ms=round(ms, 4), min_ms=round(ts[0], 4),
                           Gexp_s=round(exps / ms / 1e6, 1), mufu_frac=round(exps / ms / 1e6 / 4653, 3),
                           fused_GBs=round(fused_bytes / ms / 1e6, 1), iface_GBs=round(iface_bytes / ms / 1e6, 1),
                           env={k: v for k, v in os.environ.items() if k.startswith("MMB_")})))
