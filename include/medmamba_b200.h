@@ -195,10 +195,13 @@ int mmb_affine_cast_fwd(const void* x, const float* scale, const float* shift, v
  *   x      : (batch, 3, Hin, Win) dense, dtype in_dtype (fp32 or bf16), 16-byte aligned rows (Win % 4 == 0)
  *   weight : (embed_dim, 3, 4, 4) fp32;  conv_bias: (embed_dim) fp32 or NULL;  gamma, beta: (embed_dim) fp32
  *   out    : (batch, Hin/4, Win/4, embed_dim) fp32 dense
+ *   math_mode : 0 = fp32 FMA (bit-faithful to an fp32 convolution); 1 = the bf16 autocast arithmetic of the reference's
+ *               convolution on tensor cores: operands rounded to bf16, fp32 accumulation (mma.sync m16n8k16), bias and
+ *               LayerNorm in fp32.  Mode 1 needs fp32 images with Win / 4 <= 128 and falls back to mode 0 otherwise.
  * Hin % 4 == 0, Win % 4 == 0, embed_dim % 32 == 0, embed_dim <= 128; other shapes return MMB_ERR_UNSUPPORTED. */
 int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const float* conv_bias, const float* gamma,
                            const float* beta, float* out, int batch, int Hin, int Win, int embed_dim, float eps,
-                           int in_dtype, void* stream);
+                           int in_dtype, int math_mode, void* stream);
 
 /* Patch merging up to the norm (MedMamba.py:93-117): the 2x2 neighbourhood gather (x0, x1, x2, x3 = pixels
  * (2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1)), their concatenation and LayerNorm(4C) in one pass; odd trailing

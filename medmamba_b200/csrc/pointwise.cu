@@ -289,14 +289,14 @@ __device__ __forceinline__ F8 ld_f32x8(const float* p) {
 }
 
 template <int V, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 outnorm_gate_bf16x8_kernel(const __nv_bfloat16* __restrict__ ydir, const __nv_bfloat16* __restrict__ z,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            __nv_bfloat16* __restrict__ out, float* __restrict__ ymerged,
                            const __nv_bfloat16* __restrict__ xc, const float* __restrict__ Dsum,
                            int64_t tokens, int D, int64_t z_pix, float eps) {
     constexpr int TPW = 32 / G;
-    constexpr bool HOIST = V <= 2;                   // per-channel constants in registers for the whole token loop
+    constexpr bool HOIST = false;                    // per-channel constants stay in L1: registers buy occupancy here
     const int lane = threadIdx.x & 31, gl = lane % G;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -315,7 +315,13 @@ outnorm_gate_bf16x8_kernel(const __nv_bfloat16* __restrict__ ydir, const __nv_bf
         const bool tvalid = tok < tokens;
         const __nv_bfloat16* y0 = ydir + tok * 4 * D;
         F8 v[V];
+        uint4 zraw[V];                               // the gate travels with the slices: every load of a token in flight at once
         float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c8 = gl + G * i;
+            zraw[i] = (tvalid && c8 < C8) ? __ldg(reinterpret_cast<const uint4*>(z + tok * z_pix + 8 * c8)) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const int c8 = gl + G * i;
@@ -358,7 +364,15 @@ outnorm_gate_bf16x8_kernel(const __nv_bfloat16* __restrict__ ydir, const __nv_bf
             if (tvalid && c8 < C8) {
                 const F8 g = HOIST ? gm[i] : ld_f32x8(gamma + 8 * c8);
                 const F8 b = HOIST ? bt[i] : ld_f32x8(beta + 8 * c8);
-                const F8 zz = ld_bf16x8(z + tok * z_pix + 8 * c8);
+                F8 zz;
+                {
+                    const uint32_t w[4] = {zraw[i].x, zraw[i].y, zraw[i].z, zraw[i].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                        zz.v[2 * e] = f.x; zz.v[2 * e + 1] = f.y;
+                    }
+                }
                 F8 o;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o.v[e] = fmaf(v[i].v[e] * rstd, g.v[e], b.v[e]) * silu_f(zz.v[e]);

@@ -217,15 +217,23 @@ template <typename T> static bool aligned4(const void* p) { return reinterpret_c
 
 }  // namespace mmb
 
+int mmb_patch_embed_ln_mma(const float* x, const float* weight, const float* conv_bias, const float* gamma, const float* beta,
+                           float* out, int batch, int Hin, int Win, int embed_dim, float eps, cudaStream_t st);   // stem_mma.cu
+
 extern "C" int mmb_patch_embed_ln_fwd(const void* x, const float* weight, const float* conv_bias, const float* gamma,
                                       const float* beta, float* out, int batch, int Hin, int Win, int embed_dim,
-                                      float eps, int in_dtype, void* stream) {
+                                      float eps, int in_dtype, int math_mode, void* stream) {
     using namespace mmb;
     if (!x || !weight || !gamma || !beta || !out) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || Hin <= 0 || Win <= 0 || embed_dim <= 0) return MMB_ERR_INVALID_ARG;
     if (Hin % 4 != 0 || Win % 4 != 0 || embed_dim % 32 != 0 || embed_dim > 128) return MMB_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if (math_mode != 0 && math_mode != 1) return MMB_ERR_INVALID_ARG;
     if (batch == 0) return MMB_OK;
+    if (math_mode == 1 && in_dtype == MMB_F32 && Win / 4 <= 128 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 16 == 0)
+        return mmb_patch_embed_ln_mma(reinterpret_cast<const float*>(x), weight, conv_bias, gamma, beta, out, batch, Hin, Win,
+                                      embed_dim, eps, reinterpret_cast<cudaStream_t>(stream));
     const size_t smem = sizeof(float) * ((size_t)embed_dim * kPePitch + 12 * 4 * (size_t)kPeChunk);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long units = (long)batch * (Hin / 4) * ((Win / 4 + kPeChunk - 1) / kPeChunk);

@@ -221,9 +221,11 @@ def layernorm(x: torch.Tensor, weight, bias, eps: float, out_dtype=None) -> torc
     return out
 
 
-def patch_embed_ln(x: torch.Tensor, conv_weight, conv_bias, ln_weight, ln_bias, eps: float) -> torch.Tensor:
+def patch_embed_ln(x: torch.Tensor, conv_weight, conv_bias, ln_weight, ln_bias, eps: float, bf16_math=None) -> torch.Tensor:
     """(B, 3, Hin, Win) NCHW images -> (B, Hin/4, Win/4, E) fp32 tokens: 4x4 stride-4 convolution, permute and
-    LayerNorm in one kernel (MedMamba.py:54-76; inference; no autograd)."""
+    LayerNorm in one kernel (MedMamba.py:54-76; inference; no autograd).  ``bf16_math`` (default: whether bf16 autocast
+    is active, i.e. whether the reference's convolution would run in bf16) selects the tensor-core kernel: bf16
+    operands, fp32 accumulation; otherwise the convolution is an exact fp32 FMA chain."""
     dev = require_cuda(x, conv_weight, ln_weight, ln_bias)
     B, Cin, Hin, Win = x.shape
     E = conv_weight.shape[0]
@@ -233,10 +235,12 @@ def patch_embed_ln(x: torch.Tensor, conv_weight, conv_bias, ln_weight, ln_bias, 
     cb = None if conv_bias is None else conv_bias.detach().float().contiguous()
     g = ln_weight.detach().float().contiguous()
     bt = ln_bias.detach().float().contiguous()
+    if bf16_math is None:
+        bf16_math = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
     with torch.cuda.device(dev), timed_launch("patch_embed_ln_fwd", f"B={B},H={Hin},W={Win},E={E}"):
         st = lib().mmb_patch_embed_ln_fwd(ptr(xv), ptr(w), ptr(cb), ptr(g), ptr(bt), ptr(out), _c_int(B), _c_int(Hin),
                                           _c_int(Win), _c_int(E), ctypes.c_float(eps), _c_int(dtype_code(xv)),
-                                          stream_ptr(dev))
+                                          _c_int(int(bool(bf16_math))), stream_ptr(dev))
     check(st, "mmb_patch_embed_ln_fwd")
     return out
 

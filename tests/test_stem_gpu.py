@@ -29,6 +29,36 @@ def test_patch_embed_ln(B, Hin, Win, E, bias):
     assert_close(got16, want16, 1e-4, 1e-5, "patch_embed_ln bf16 input")
 
 
+@pytest.mark.parametrize("B,Hin,Win,E", [(2, 224, 224, 96), (1, 512, 512, 96), (3, 40, 24, 32), (2, 36, 72, 64), (1, 4, 4, 128),
+                                         (2, 20, 512, 96), (5, 12, 8, 96), (1, 28, 516, 96)])
+@pytest.mark.parametrize("bias", [True, False])
+def test_patch_embed_ln_tensor_core_path(B, Hin, Win, E, bias):
+    """math_mode 1 (what bf16 autocast selects): operands rounded to bf16, fp32 accumulation on HMMA, bias + LayerNorm in
+    fp32 -- against the fp64 convolution of the SAME bf16-rounded operands (the only difference left is the fp32
+    accumulation order), strips that straddle token rows, ragged last strips, and the > 128 tokens-per-row fall-back."""
+    from medmamba_b200 import ops
+    g = torch.Generator().manual_seed(Hin + Win + E)
+    x = torch.randn(B, 3, Hin, Win, generator=g)
+    w = torch.randn(E, 3, 4, 4, generator=g) * 0.2
+    cb = torch.randn(E, generator=g) if bias else None
+    gm, bt = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    q = lambda t: t.bfloat16().double()
+    fallback = Win // 4 > 128
+    want = F.conv2d(x.double() if fallback else q(x), w.double() if fallback else q(w), None if cb is None else cb.double(),
+                    stride=4).permute(0, 2, 3, 1)
+    want = F.layer_norm(want, (E,), gm.double(), bt.double(), 1e-5)
+    got = ops.patch_embed_ln(x.cuda(), w.cuda(), None if cb is None else cb.cuda(), gm.cuda(), bt.cuda(), 1e-5, bf16_math=True)
+    assert got.shape == (B, Hin // 4, Win // 4, E) and got.dtype == torch.float32
+    assert_close(got, want, 1e-4, 1e-5, "patch_embed_ln tensor-core path")
+    # and it is what the module picks under bf16 autocast, within bf16 accuracy of the exact convolution
+    exact = F.layer_norm(F.conv2d(x.double(), w.double(), None if cb is None else cb.double(), stride=4).permute(0, 2, 3, 1),
+                         (E,), gm.double(), bt.double(), 1e-5)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        auto = ops.patch_embed_ln(x.cuda(), w.cuda(), None if cb is None else cb.cuda(), gm.cuda(), bt.cuda(), 1e-5)
+    assert torch.equal(auto, got)
+    assert (auto.double().cpu() - exact).abs().max().item() < 3e-2 * max(1.0, exact.abs().max().item())
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 96), (1, 7, 9, 8), (2, 28, 28, 192), (1, 14, 14, 384), (3, 5, 6, 20),
                                      (1, 4, 4, 512)])
 def test_patch_merge_ln(B, H, W, C):
