@@ -176,7 +176,8 @@ class SelectiveScanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                 return_last_state=False):
-        needs_grad = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, z, delta_bias))
+        # under no_grad nothing needs the checkpoints even if the inputs are leaves that require grad
+        needs_grad = any(ctx.needs_input_grad)
         out, last, chunk_state = scan_forward(
             u, delta, A, B, C, D, z, delta_bias, delta_softplus,
             want_last_state=return_last_state, want_chunk_state=needs_grad)

@@ -26,6 +26,16 @@ def timeit(fn):
     return ts[len(ts) // 2]
 
 
+g = torch.Generator(device="cuda").manual_seed(9)
+img = torch.randn(B, 3, 224, 224, device="cuda", generator=g)
+cw = torch.randn(96, 3, 4, 4, device="cuda", generator=g) * 0.2
+cb, lw, lb = torch.randn(96, device="cuda", generator=g), torch.ones(96, device="cuda"), torch.zeros(96, device="cuda")
+pe_bytes = B * (3 * 224 * 224 * 4 + 56 * 56 * 96 * 4)
+for name, mode in (("patch_embed_ln_fp32_fma", False), ("patch_embed_ln_bf16_mma", True)):
+    ms = timeit(lambda: ops.patch_embed_ln(img, cw, cb, lw, lb, 1e-5, bf16_math=mode))
+    print(json.dumps(dict(stage=0, batch=B, kernel=name, ms=round(ms, 4), GBs=round(pe_bytes / ms / 1e6, 1))))
+del img
+
 for si, (H, D) in enumerate(((56, 96), (28, 192), (14, 384), (7, 768))):
     g = torch.Generator(device="cuda").manual_seed(si)
     tok = B * H * H
