@@ -307,14 +307,23 @@ def scan_microbench_record(mm, dev, peak, batch=64, iters=10):
     import math
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = []
-    for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+    for dtype, name, layout in ((torch.float32, "f32", "contiguous"), (torch.float32, "f32", "call_site"),
+                                (torch.bfloat16, "bf16", "contiguous")):
         for KD, L in STAGE_SHAPES:
             g = torch.Generator(device=dev).manual_seed(KD + L)
             rn = lambda *s: torch.randn(*s, device=dev, generator=g)
             u = (0.1 * rn(batch, KD, L)).to(dtype).requires_grad_()
             delta = (0.03 * rn(batch, KD, L)).to(dtype).requires_grad_()
             A = (-torch.arange(1, N_STATE + 1, device=dev, dtype=torch.float32)).repeat(KD, 1).requires_grad_()
-            Bm, Cm = (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_(), (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_()
+            if layout == "contiguous":
+                Bm, Cm = (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_(), (0.05 * rn(batch, K_DIR, N_STATE, L)).requires_grad_()
+            else:
+                # what MedMamba.py:259-261, 267-268 hands over: slices of the x_proj einsum output, N-contiguous with
+                # stride(-1) = dt_rank + 2 * d_state
+                R = -(-(KD // K_DIR // 2) // 16)
+                xdbl = (0.05 * rn(batch, K_DIR, L, R + 2 * N_STATE)).requires_grad_()
+                Bm = xdbl[..., R:R + N_STATE].permute(0, 1, 3, 2)
+                Cm = xdbl[..., R + N_STATE:].permute(0, 1, 3, 2)
             D = torch.ones(KD, device=dev, requires_grad=True)
             dt = torch.exp(torch.rand(KD, device=dev, generator=g) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
             bias = (dt + torch.log(-torch.expm1(-dt))).requires_grad_()
@@ -327,11 +336,11 @@ def scan_microbench_record(mm, dev, peak, batch=64, iters=10):
                     return mm.selective_scan_fn(u, delta, A, Bm, Cm, D, None, bias, True)
 
             def fwd_bwd():
-                for t in (u, delta, A, Bm, Cm, D, bias):
+                for t in (u, delta, A, Bm, Cm, D, bias) + ((xdbl,) if layout != "contiguous" else ()):
                     t.grad = None
                 mm.selective_scan_fn(u, delta, A, Bm, Cm, D, None, bias, True).backward(dout)
 
-            rec = {"dtype": name, "KD": KD, "L": L, "batch": batch}
+            rec = {"dtype": name, "KD": KD, "L": L, "batch": batch, "bc_layout": layout}
             for label, fn, nbytes in (("fwd", fwd, fwd_bytes), ("fwd_bwd", fwd_bwd, 3 * fwd_bytes)):
                 for _ in range(3):
                     fn()

@@ -26,6 +26,7 @@ struct ScanFwdParams {
     const void* u; const void* delta; const void* Bm; const void* Cm; const void* z; void* out;
     const float* A; const float* Dv; const float* bias; float* last_state; float* chunk_state;
     int batch, dim, L, N, G, H, nchunks, softplus;
+    int flags;       // async path: bit 0 = u / delta rows take 16-byte pieces, bit 1 = B / C rows do
     int64_t u_bs, u_ds, d_bs, d_ds, z_bs, z_ds, o_bs, o_ds;
     int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
 };
@@ -242,6 +243,11 @@ __global__ void __launch_bounds__(128) scan_fwd_kernel(const ScanFwdParams p) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
+// 4-byte pieces for rows that are only element-aligned (L = 49) and for B / C views with an arbitrary step stride
+// (the reference's call site passes stride(-1) = dt_rank + 2 * d_state, MedMamba.py:261, 267-268)
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -275,26 +281,52 @@ __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams
     }
     const float Dd = (valid && p.Dv) ? p.Dv[d] : 0.f;
 
+    // 16-byte pieces when every row starts 16-byte aligned and runs along L; 4-byte pieces otherwise
+    const bool vec_ud = (p.flags & 1) != 0, vec_bc = (p.flags & 2) != 0;
     auto prefetch = [&](int c) {
         float* base = smem + (c & 1) * BUF;
         float* su = base, *sd = su + RT * TP, *sB = sd + RT * TP, *sC = sB + kMaxState * TP;
         const int t0 = c * T, len = min(T, p.L - t0);
-        for (int idx = tid; idx < RT * T4; idx += NT) {
-            const int rr = idx / T4, tt = (idx % T4) * 4;
-            const bool rok = rr < rows_here;
-            const int64_t dd = g * p.H + row0 + (rok ? rr : 0);
-            const int nb = rok ? max(0, min(4, len - tt)) * 4 : 0;
-            const int ts = nb ? t0 + tt : 0;                       // keep the (unused) source address inside the row
-            cp_async16(su + rr * TP + tt, ub + dd * p.u_ds + ts, nb);
-            cp_async16(sd + rr * TP + tt, db + dd * p.d_ds + ts, nb);
+        if (vec_ud) {
+            for (int idx = tid; idx < RT * T4; idx += NT) {
+                const int rr = idx / T4, tt = (idx % T4) * 4;
+                const bool rok = rr < rows_here;
+                const int64_t dd = g * p.H + row0 + (rok ? rr : 0);
+                const int nb = rok ? max(0, min(4, len - tt)) * 4 : 0;
+                const int ts = nb ? t0 + tt : 0;                       // keep the (unused) source address inside the row
+                cp_async16(su + rr * TP + tt, ub + dd * p.u_ds + ts, nb);
+                cp_async16(sd + rr * TP + tt, db + dd * p.d_ds + ts, nb);
+            }
+        } else {
+            for (int idx = tid; idx < RT * T; idx += NT) {
+                const int rr = idx / T, tt = idx % T;
+                const bool ok = rr < rows_here && tt < len;
+                const int64_t dd = g * p.H + row0 + (ok ? rr : 0);
+                const int ts = ok ? t0 + tt : 0;
+                cp_async4(su + rr * TP + tt, ub + dd * p.u_ds + ts, ok ? 4 : 0);
+                cp_async4(sd + rr * TP + tt, db + dd * p.d_ds + ts, ok ? 4 : 0);
+            }
         }
-        for (int idx = tid; idx < kMaxState * T4; idx += NT) {
-            const int n = idx / T4, tt = (idx % T4) * 4;
-            const int nb = n < p.N ? max(0, min(4, len - tt)) * 4 : 0;
-            const int ts = nb ? t0 + tt : 0;
-            const int nn = n < p.N ? n : 0;
-            cp_async16(sB + n * TP + tt, Bb + (int64_t)nn * p.B_ns + ts, nb);
-            cp_async16(sC + n * TP + tt, Cb + (int64_t)nn * p.C_ns + ts, nb);
+        if (vec_bc) {
+            for (int idx = tid; idx < kMaxState * T4; idx += NT) {
+                const int n = idx / T4, tt = (idx % T4) * 4;
+                const int nb = n < p.N ? max(0, min(4, len - tt)) * 4 : 0;
+                const int ts = nb ? t0 + tt : 0;
+                const int nn = n < p.N ? n : 0;
+                cp_async16(sB + n * TP + tt, Bb + (int64_t)nn * p.B_ns + ts, nb);
+                cp_async16(sC + n * TP + tt, Cb + (int64_t)nn * p.C_ns + ts, nb);
+            }
+        } else {
+            // any element strides; the unit-stride index runs fastest over the threads (n for the call-site views)
+            const bool n_fast = p.B_ns == 1 && p.B_ls != 1;
+            for (int idx = tid; idx < kMaxState * T; idx += NT) {
+                const int n = n_fast ? idx % kMaxState : idx / T, tt = n_fast ? idx / kMaxState : idx % T;
+                const bool ok = n < p.N && tt < len;
+                const int64_t off_b = ok ? (int64_t)n * p.B_ns + (int64_t)(t0 + tt) * p.B_ls : 0;
+                const int64_t off_c = ok ? (int64_t)n * p.C_ns + (int64_t)(t0 + tt) * p.C_ls : 0;
+                cp_async4(sB + n * TP + tt, Bb + off_b, ok ? 4 : 0);
+                cp_async4(sC + n * TP + tt, Cb + off_c, ok ? 4 : 0);
+            }
         }
         cp_async_commit();
     };
@@ -421,14 +453,17 @@ static int launch_scan_fwd_async(const ScanFwdParams& p, cudaStream_t stream) {
     return launch_status();
 }
 
-// cp.async needs 16-byte aligned, L-contiguous fp32 rows for u, delta, B and C
-static bool async_path_ok(const ScanFwdParams& p, int io_dtype, int bc_dtype) {
+// The cp.async path takes any fp32 layout the operator accepts (unit stride along L for u / delta, any strides for
+// B / C): 16-byte pieces where rows are 16-byte aligned and L-contiguous, 4-byte pieces otherwise.
+static bool async_path_ok(ScanFwdParams& p, int io_dtype, int bc_dtype) {
     if (io_dtype != MMB_F32 || bc_dtype != MMB_F32 || p.chunk_state) return false;
     if (getenv("MMB_SCAN_SYNC")) return false;
-    const auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-    if (!al(p.u) || !al(p.delta) || !al(p.Bm) || !al(p.Cm)) return false;
-    if (p.u_ds % 4 || p.u_bs % 4 || p.d_ds % 4 || p.d_bs % 4) return false;
-    if (p.B_ls != 1 || p.C_ls != 1 || p.B_ns % 4 || p.C_ns % 4 || p.B_bs % 4 || p.C_bs % 4 || p.B_gs % 4 || p.C_gs % 4) return false;
+    const auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
+    if (!al(p.u, 4) || !al(p.delta, 4) || !al(p.Bm, 4) || !al(p.Cm, 4)) return false;
+    p.flags = 0;
+    if (al(p.u, 16) && al(p.delta, 16) && p.u_ds % 4 == 0 && p.u_bs % 4 == 0 && p.d_ds % 4 == 0 && p.d_bs % 4 == 0) p.flags |= 1;
+    if (al(p.Bm, 16) && al(p.Cm, 16) && p.B_ls == 1 && p.C_ls == 1 && p.B_ns % 4 == 0 && p.C_ns % 4 == 0 && p.B_bs % 4 == 0 &&
+        p.C_bs % 4 == 0 && p.B_gs % 4 == 0 && p.C_gs % 4 == 0) p.flags |= 2;
     return true;
 }
 
@@ -505,7 +540,7 @@ extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, co
     p.u = u; p.delta = delta; p.Bm = Bm; p.Cm = Cm; p.z = z; p.out = out;
     p.A = A; p.Dv = Dv; p.bias = delta_bias; p.last_state = last_state; p.chunk_state = chunk_state;
     p.batch = batch; p.dim = dim; p.L = seqlen; p.N = dstate; p.G = ngroups; p.H = dim / ngroups;
-    p.softplus = delta_softplus;
+    p.softplus = delta_softplus; p.flags = 0;
     p.u_bs = u_bs; p.u_ds = u_ds; p.d_bs = delta_bs; p.d_ds = delta_ds;
     p.z_bs = z_bs; p.z_ds = z_ds; p.o_bs = out_bs; p.o_ds = out_ds;
     p.B_bs = B_bs; p.B_gs = B_gs; p.B_ns = B_ns; p.B_ls = B_ls;
