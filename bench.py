@@ -268,7 +268,7 @@ def max_ms(values, dev, dist):
 
 
 # --------------------------------------------------------------------------------------- sub-records
-def infer_config_record(mm, ops, dev, dist, world, batch, res, dtype, steps, peak, label):
+def infer_config_record(mm, ops, dev, dist, world, batch, res, dtype, steps, peak, label, graph=False):
     """A short inference measurement of another BASELINE config (fresh model, own warm-up), device-resident inputs."""
     tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     if dtype == "f32":
@@ -293,6 +293,17 @@ def infer_config_record(mm, ops, dev, dist, world, batch, res, dtype, steps, pea
         rec = {"workload": label, "dtype": dtype, "batch_per_gpu": batch, "res": res, "steps": steps,
                "ms_per_step": round(ms / steps, 3), "value": round(world * batch * steps / (ms / 1e3), 1), "unit": UNIT,
                "gpu_launches": timer.launches, "roofline_stages": core_rooflines(ks, batch, res, dtype, peak)}
+        if graph:
+            # the same forward captured once as a CUDA graph (medmamba_b200.GraphedForward, what InferencePipeline uses
+            # for small batches): at this size the eager step is bound by the ~250 launches, not by the kernels
+            gf = mm.GraphedForward(net, x, torch.bfloat16 if dtype == "bf16" else None)
+            for _ in range(3):
+                gf.replay()
+            msg, _ = timed_loop(gf.replay, steps * 4, dist)
+            msg = max_ms([msg], dev, dist)[0]
+            rec["cuda_graph"] = {"ms_per_step": round(msg / (steps * 4), 3),
+                                 "value": round(world * batch * steps * 4 / (msg / 1e3), 1), "unit": UNIT}
+            del gf
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     del net, x
@@ -341,21 +352,23 @@ def scan_microbench_record(mm, dev, peak, batch=64, iters=10):
                 mm.selective_scan_fn(u, delta, A, Bm, Cm, D, None, bias, True).backward(dout)
 
             rec = {"dtype": name, "KD": KD, "L": L, "batch": batch, "bc_layout": layout}
+            from medmamba_b200 import ops as _ops
             for label, fn, nbytes in (("fwd", fwd, fwd_bytes), ("fwd_bwd", fwd_bwd, 3 * fwd_bytes)):
                 for _ in range(3):
                     fn()
-                tot = 0.0
+                # kernel time: CUDA events either side of each C-ABI launch (the Python wrapper of a 0.1-1 ms kernel would
+                # otherwise show up as idle GPU time between the events)
+                timer = _ops.KernelTimer()
+                _ops.set_kernel_timer(timer)
                 for _ in range(iters):
                     flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
                     fn()
-                    e1.record()
-                    torch.cuda.synchronize()
-                    tot += e0.elapsed_time(e1)
-                ms = tot / iters
+                _ops.set_kernel_timer(None)
+                ks = timer.summary()
+                ms = sum(v["total_ms"] for k, v in ks.items() if k.startswith("scan_")) / iters
                 rec[label] = {"ms": round(ms, 4), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
-                              "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+                              "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4),
+                              "kernels": {k.split("[")[0]: round(v["avg_ms"], 4) for k, v in ks.items() if k.startswith("scan_")}}
             out.append(rec)
     del flush
     torch.cuda.empty_cache()
@@ -495,7 +508,7 @@ def run_ours(args):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
         cfgs = {}
         cfgs["configs[0]"] = infer_config_record(mm, ops, dev, dist, world, 8, 224, "f32", 10, peak,
-                                                 "MedMamba-T fp32 forward, batch 8, 224x224 (BASELINE configs[0])")
+                                                 "MedMamba-T fp32 forward, batch 8, 224x224 (BASELINE configs[0])", graph=True)
         cfgs["configs[4]"] = infer_config_record(mm, ops, dev, dist, world, 32, 512, "bf16", 5, peak,
                                                  "MedMamba-T 512x512 inference, batch 32, stage-1 L = 16384 (BASELINE configs[4])")
         if rank == 0 and world == 1:

@@ -31,10 +31,9 @@ def side_stream(device) -> "torch.cuda.Stream":
 
 
 def branch_overlap_enabled() -> bool:
-    """MMB_BRANCH_OVERLAP=0 keeps both branches of a block on one stream (debugging / A-B timing);
-    stream capture (CUDA graphs) also disables the side stream."""
-    import os
-    return os.environ.get("MMB_BRANCH_OVERLAP", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+    """MMB_BRANCH_OVERLAP=0 keeps both branches of a block on one stream (debugging / A-B timing).  Under stream
+    capture (CUDA graphs) the side stream stays: wait_stream records the fork / join as graph dependencies."""
+    return os.environ.get("MMB_BRANCH_OVERLAP", "1") != "0"
 
 
 def fused_available() -> bool:

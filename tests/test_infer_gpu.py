@@ -25,6 +25,29 @@ def test_pipeline_matches_direct_calls():
     assert list(pipe.stream([])) == []
 
 
+@pytest.mark.parametrize("amp", [None, torch.bfloat16])
+def test_graphed_forward_replays_the_eager_forward(amp):
+    """GraphedForward: the forward captured as one CUDA graph (the two-stream branch overlap included) returns, for new
+    contents of its static input, exactly what the eager forward returns."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.VSSM(depths=[1, 2], dims=[32, 64], num_classes=5).cuda().eval()
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    gf = mm.GraphedForward(net, x, amp)
+    for seed in (1, 2, 3):
+        x.copy_(torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(seed)))
+        got = gf.replay().clone()
+        with torch.no_grad(), torch.autocast("cuda", dtype=amp or torch.bfloat16, enabled=amp is not None):
+            want = net(x)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    # the pipeline picks the graph for small batches on its own and the eager path when told to
+    batches = [torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(10 + i)).pin_memory() for i in range(4)]
+    a = list(mm.InferencePipeline(net, autocast_dtype=amp, cuda_graph="auto").stream(batches))
+    b = list(mm.InferencePipeline(net, autocast_dtype=amp, cuda_graph=False).stream(batches))
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
 def test_pipeline_rejects_cpu_module():
     import medmamba_b200 as mm
     with pytest.raises(RuntimeError):
