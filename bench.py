@@ -375,7 +375,7 @@ def scan_microbench_record(mm, dev, peak, batch=64, iters=10):
     return out
 
 
-def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf16"):
+def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf16", kernel_times=False):
     """BASELINE configs[3]: data-parallel training step (CE + AdamW, train.py:187-192, 277-288), batch per GPU, the
     gradient average as NCCL all-reduces over flat buckets launched from gradient hooks during backward."""
     torch.manual_seed(0)                                   # identical replicas
@@ -406,11 +406,12 @@ def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf
 
     for _ in range(3):
         step()
-    timer = ops.KernelTimer(timing=False)
+    timer = ops.KernelTimer(timing=kernel_times)
     ops.set_kernel_timer(timer)
     ms, loss = timed_loop(step, steps, dist)
     ops.set_kernel_timer(None)
     fired = red.launched_in_backward
+    kstats = timer.summary() if kernel_times else None
     ms_noex = None
     if world > 1:
         exchange[0] = False
@@ -429,7 +430,9 @@ def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf
                "ms_per_step_without_exchange": round(ms_noex / steps, 3),
                "allreduce_exposed_ms": round((ms - ms_noex) / steps, 3),
                "exposed_share_of_step": round((ms - ms_noex) / ms, 4)},
-           "loss": round(float(loss), 4)}
+           "loss": round(float(loss.detach()), 4)}
+    if kstats:
+        rec["kernels"] = {k: {"avg_ms": round(v["avg_ms"], 4), "count": v["count"]} for k, v in sorted(kstats.items())}
     red.close()
     del net, opt, red, x, y
     torch.cuda.empty_cache()
@@ -571,7 +574,7 @@ def run_train(args):
     dist = torch.distributed if world > 1 else None
     torch.backends.cudnn.benchmark = True
     sampler = ClockSampler(local) if rank == 0 else None
-    rec = train_record(mm, ops, mdist, dev, dist, rank, world, args.batch, args.steps, args.dtype)
+    rec = train_record(mm, ops, mdist, dev, dist, rank, world, args.batch, args.steps, args.dtype, kernel_times=True)
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         print(json.dumps({
@@ -579,7 +582,8 @@ def run_train(args):
             "warmup": 3, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": rec["workload"], "global_batch": rec["global_batch"], "parallelism": rec["parallelism"]},
-            "gpu_launches": rec["gpu_launches"], "clocks": clocks, "allreduce": rec["allreduce"], "loss": rec["loss"]}),
+            "gpu_launches": rec["gpu_launches"], "clocks": clocks, "allreduce": rec["allreduce"], "loss": rec["loss"],
+            "kernels": rec.get("kernels")}),
             flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -218,8 +218,9 @@ int mmb_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta,
 /* Rows of the partial buffers of mmb_outnorm_gate_bwd and mmb_dwconv3x3_silu_bwd_ds (host only). */
 int mmb_partial_blocks(void);
 
-/* Channel tiles mmb_ss2d_core_bwd cuts D into (host only): leading extent of dBC_part. */
-int mmb_ss2d_core_bwd_tiles(int D);
+/* Channel groups (one per warp: 32 or 16 channels, by launch size) whose dproj partials mmb_ss2d_core_bwd writes for this
+ * problem (host only): the leading extent of dproj_part.  Every partial row is written; nothing needs a memset. */
+int mmb_ss2d_core_bwd_tiles(int batch, int D);
 
 /* Gradient of mmb_ss2d_core_fwd given dY (batch, H, W, D) fp32 -- the gradient of the merged sum, identical for
  * the four direction slices of ydir.  xc, proj, Wdt, dt_bias, A, Ds as in the forward; hsave as written by it.

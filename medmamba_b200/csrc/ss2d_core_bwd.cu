@@ -11,10 +11,14 @@
 //   phase A  re-run the half block forward, parking h_{t-1} of every step in the warp's shared-memory history;
 //   phase B  the reverse recurrence g_t = dy_t C_t + a_{t+1} g_{t+1} and all gradients (a_t recomputed).
 // That is 2.5 forward passes of exps; the MUFU pipe has room (the cost of a backward is instructions).
-// dB_n / dC_n / d dt_r need a sum over the channels of the (batch, direction): each warp transposes its 32
-// lanes x (32 + RP) values through shared memory so that lane v owns the sum of value v, and stores one
-// partial row per 32-channel group to HBM (coalesced); the host adds the groups.  dA, dD, dWdt, d dt_bias are
-// per-thread accumulators, one partial per batch element.  No float atomics: bit-reproducible.
+// dB_n / dC_n / d dt_r need a sum over the channels of the (batch, direction).  Each warp reduces its lanes' 32 + RP
+// values per step with a shuffle butterfly (a reduce-scatter: at every stage a lane keeps one half of its values and
+// sends the other; the pairing order -- dB_n with dC_n first, then adjacent states -- lets every stage run as soon as
+// its two operands exist, so the values never pile up in registers) and lane v stores the warp's sum of value v: one
+// partial row per warp-sized channel group to HBM, the host adds the groups.  Round 1 transposed the values through
+// shared memory instead: 36-56 STS + 8-16 LDS.128 per step against 31-37 SHFL now, and the 5 KB tile per warp was what
+// kept a fourth CTA off the SM.  dA, dD, dWdt, d dt_bias are per-thread accumulators, one partial per batch element.
+// No float atomics: bit-reproducible.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -39,23 +43,27 @@ struct CoreBwdParams {
     int T_row, NB_row, nw, T_col, NI_col, NO_col, cap;
 };
 
+// keep `hi ? b : a` and exchange the other one with the lane `mask` away: one stage of the reduce-scatter butterfly
+__device__ __forceinline__ float bfly(const float a, const float b, const bool hi, const int mask) {
+    const float send = hi ? a : b, keep = hi ? b : a;
+    return keep + __shfl_xor_sync(0xffffffffu, send, mask);
+}
+
 template <int S, int RP, typename xc_t>
-__global__ void __launch_bounds__(96, S == 1 ? 3 : 5)
+__global__ void __launch_bounds__(96, S == 1 ? 4 : 5)
 ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_constant__ CUtensorMap tmx_col,
                      const __grid_constant__ CUtensorMap tmd_row, const __grid_constant__ CUtensorMap tmd_col,
                      const __grid_constant__ CUtensorMap tmp_row, const __grid_constant__ CUtensorMap tmp_col,
                      const CoreBwdParams p) {
     constexpr int NS = kMaxState / S, CP = 32 + RP, TB = kTrainCap, XE = (int)sizeof(xc_t);
     constexpr int CW = 32 / S;                 // channels per warp
-    constexpr int TP = CW + 4;                 // row pitch (floats) of the transposition tile: conflict-free LDS.128
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int xpad = (p.cap * p.CT * XE + 127) & ~127, dpad = (p.cap * p.CT * 4 + 127) & ~127,
               ppad = (p.cap * CP * 4 + 127) & ~127;
     const int stage_bytes = xpad + dpad + ppad;
     const int nwarps = blockDim.x >> 5;
     float* shist = reinterpret_cast<float*>(smem_raw + kBwdStages * stage_bytes);     // [nwarps][kHalf][16][32]
-    float* strn = shist + nwarps * kHalf * NS * 32;                                   // [nwarps][CP][TP]
-    float* sstp = strn + nwarps * CP * TP;                                       // [nwarps][TB][3][32]
+    float* sstp = shist + nwarps * kHalf * NS * 32;                                   // [nwarps][TB][3][32]
     uint64_t* full = reinterpret_cast<uint64_t*>(sstp + nwarps * TB * 3 * 32);
     uint64_t* empty = full + kBwdStages;
 
@@ -114,9 +122,18 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     float dD_acc = 0.f, db_acc = 0.f;
     const int64_t gstride = 4 * (int64_t)p.D;
     float* dub = p.dudir + ((int64_t)b * p.L * 4 + k) * p.D + c;
-    float* dpb = p.dproj + (((int64_t)(gvalid ? group : 0) * p.B + b) * p.L * 4 + k) * CP + lane;
+    // value this lane owns after the butterflies: [0,16) dB_n, [16,32) dC_n with the state bits spread over the lane
+    // bits from high to low (lane bit 4 = dB / dC, bit 3 = n bit 0, bit 2 = n bit 1, bit 1 = n bit 2, bit 0 = n bit 3;
+    // with two lanes per channel bit 0 is the state half q instead)
+    const int vown = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) + 2 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1) + 8 * (lane & 1);
+    constexpr int RP2 = RP <= 4 ? 4 : (RP <= 8 ? 8 : (RP <= 16 ? 16 : 32));      // dt_r values padded to a power of two
+    constexpr int RLG = RP2 == 4 ? 2 : (RP2 == 8 ? 3 : (RP2 == 16 ? 4 : 5));
+    int rown = 0;                                                               // dt_r index this lane owns
+#pragma unroll
+    for (int i = 0; i < RLG; ++i) rown |= ((lane >> (4 - i)) & 1) << i;
+    const bool rwriter = (lane & ((32 >> RLG) - 1)) == 0 && rown < RP;
+    float* dpb = p.dproj + (((int64_t)(gvalid ? group : 0) * p.B + b) * p.L * 4 + k) * CP;
     float* hist = shist + warp * kHalf * NS * 32 + lane;        // [tl][j] at (tl * 16 + j) * 32
-    float* trn = strn + warp * CP * TP;                         // [v][col] at v * TP + col
     float* stp = sstp + warp * TB * 3 * 32 + lane;              // per-step delta / d softplus / u of this lane
     const float* hck = p.hsave + (((int64_t)b * 4 + k) * p.NBmax * p.D + (cvalid ? c : 0)) * kMaxState + q * NS;   // + (jb-1) * D * 16
 
@@ -226,12 +243,13 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             const float dli = stp[(tl * 3 + 0) * 32], sgi = stp[(tl * 3 + 1) * 32], u = stp[(tl * 3 + 2) * 32];
             const float dlu = dli * u;
             float adu[2] = {0.f, 0.f}, adA[2] = {0.f, 0.f};
+            float yg[NS / 4];                     // per group of 4 states: the butterfly's partial after three stages
 #pragma unroll
             for (int j4 = 0; j4 < NS / 4; ++j4) {
                 const float4 bv = bp[j4], cv = bp[4 + j4];
                 const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
                 const int j = 4 * j4;
-                float hp[4], a[4], x[4];
+                float hp[4], a[4], x[4], xp[2];
                 mul2(x[0], x[1], dli, dli, Ap[j], Ap[j + 1]);
                 mul2(x[2], x[3], dli, dli, Ap[j + 2], Ap[j + 3]);
 #pragma unroll
@@ -252,9 +270,19 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                     mul2(ga0, ga1, a[e], a[e + 1], gt0, gt1);
                     gcar[j + e] = ok ? ga0 : gcar[j + e];
                     gcar[j + e + 1] = ok ? ga1 : gcar[j + e + 1];
-                    trn[(q * NS + j + e) * TP + col] = vb0; trn[(q * NS + j + e + 1) * TP + col] = vb1;
-                    trn[(16 + q * NS + j + e) * TP + col] = vc0; trn[(16 + q * NS + j + e + 1) * TP + col] = vc1;
+                    // butterfly stages 1 (dB_n | dC_n over lane bit 4) and 2 (the two states of the pair over bit 3)
+                    const float u0 = bfly(vb0, vc0, (lane & 16) != 0, 16), u1 = bfly(vb1, vc1, (lane & 16) != 0, 16);
+                    xp[e >> 1] = bfly(u0, u1, (lane & 8) != 0, 8);
                 }
+                yg[j4] = bfly(xp[0], xp[1], (lane & 4) != 0, 4);                               // stage 3: state bit 1
+            }
+            // stages 4 and 5: state bits 2 and 3 (two lanes per channel: bit 3 is the lane's own half q, no exchange)
+            float vsum;
+            if constexpr (S == 1) {
+                const float z0 = bfly(yg[0], yg[1], (lane & 2) != 0, 2), z1 = bfly(yg[2], yg[3], (lane & 2) != 0, 2);
+                vsum = bfly(z0, z1, (lane & 1) != 0, 1);
+            } else {
+                vsum = bfly(yg[0], yg[1], (lane & 2) != 0, 2);
             }
             float su = adu[0] + adu[1], sa = adA[0] + adA[1];
 #pragma unroll
@@ -271,7 +299,11 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 dD_acc = fmaf(dy, u, dD_acc);
             }
             db_acc += ddr;
+            // d dt_r = sum over the channels of Wdt[c][r] * d delta_raw[c]: the same butterfly over the RP2 padded values
+            // (adjacent r first), then plain exchanges over the lane bits that are left
+            const float ddq = q == 0 ? ddr : 0.f;                          // one contribution per channel
             const float4* dtp = reinterpret_cast<const float4*>(ps + sl * CP + 32);
+            float tr[RP2];
 #pragma unroll
             for (int r4 = 0; r4 < RP / 4; ++r4) {
                 const float4 v = dtp[r4];
@@ -279,26 +311,26 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     dWd[4 * r4 + e] = fmaf(ddr, dt4[e], dWd[4 * r4 + e]);
-                    if (q == 0) trn[(32 + 4 * r4 + e) * TP + col] = Wd[4 * r4 + e] * ddr;
+                    tr[4 * r4 + e] = Wd[4 * r4 + e] * ddq;
                 }
             }
-            __syncwarp();
-            // lane v sums row v over the warp's channels: [0,16) dB_n, [16,32) dC_n; rows 32.. are d dt_r
-            {
-                const float4* rowp = reinterpret_cast<const float4*>(trn + lane * TP);
-                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < CW / 4; ++i) { const float4 v = rowp[i]; s0 += v.x + v.y; s1 += v.z + v.w; }
-                if (ok && gvalid) dpb[(int64_t)pos * 4 * CP] = s0 + s1;
-                if (lane < RP) {
-                    const float4* rowq = reinterpret_cast<const float4*>(trn + (32 + lane) * TP);
-                    float q0 = 0.f, q1 = 0.f;
+            for (int r = RP; r < RP2; ++r) tr[r] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < CW / 4; ++i) { const float4 v = rowq[i]; q0 += v.x + v.y; q1 += v.z + v.w; }
-                    if (ok && gvalid) dpb[(int64_t)pos * 4 * CP + 32] = q0 + q1;
-                }
+            for (int lv = 0; lv < RLG; ++lv) {
+                const int mask = 16 >> lv;
+#pragma unroll
+                for (int i = 0; i < (RP2 >> (lv + 1)); ++i) tr[i] = bfly(tr[2 * i], tr[2 * i + 1], (lane & mask) != 0, mask);
             }
-            __syncwarp();
+            float rsum = tr[0];
+#pragma unroll
+            for (int mask = 16 >> RLG; mask > 0; mask >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, mask);
+            if (ok && gvalid) {
+                float* dpr = dpb + (int64_t)pos * 4 * CP;
+                if (S == 1) dpr[vown] = vsum;
+                else dpr[((lane >> 4) & 1) * 16 + q * NS + ((lane >> 3) & 1) + 2 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1)] = vsum;
+                if (rwriter) dpr[32 + rown] = rsum;
+            }
         };
 
         float h[NS];
@@ -335,11 +367,12 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     }
 }
 
-// lanes per channel: 2 unless the launch has many more warps than the machine holds (thin warps hide the
-// latency of the reverse step better; S = 1 has the fewest instructions)
+// lanes per channel: one (the fewest instructions; four CTAs of three warps per SM) as soon as the launch fills most of
+// one round of resident CTAs, two for smaller launches (thin warps hide the latency of the reverse step better)
 static int core_bwd_split(int B, int D) {
     if (const char* e = getenv("MMB_BWD_S")) { const int v = atoi(e); if (v == 1 || v == 2) return v; }
-    return (4L * B * D >= 32L * 40 * num_sms()) ? 1 : 2;
+    const long ctas1 = 4L * B * ((D + 95) / 96);
+    return ctas1 * 10 >= 6L * 4 * num_sms() ? 1 : 2;
 }
 // channels per CTA: one warp per 32/S-channel group, up to three warps, chosen to divide the group count
 static int core_bwd_ct(int D, int S) {
@@ -383,7 +416,7 @@ static int launch_core_bwd(CoreBwdParams& p, const void* xc, const float* dY, co
     const int threads = p.CT * S, nwarps = threads / 32;
     const size_t xpad = ((size_t)p.cap * p.CT * XE + 127) & ~(size_t)127, dpad = ((size_t)p.cap * p.CT * 4 + 127) & ~(size_t)127,
                  ppad = ((size_t)p.cap * CP * 4 + 127) & ~(size_t)127;
-    const size_t smem = kBwdStages * (xpad + dpad + ppad) + (size_t)nwarps * (kHalf * (kMaxState / S) * 32 + CP * (32 / S + 4) + kTrainCap * 3 * 32) * 4 +
+    const size_t smem = kBwdStages * (xpad + dpad + ppad) + (size_t)nwarps * (kHalf * (kMaxState / S) * 32 + kTrainCap * 3 * 32) * 4 +
                         2 * kBwdStages * sizeof(uint64_t);
     auto kern = ss2d_core_bwd_kernel<S, RP, xc_t>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -408,9 +441,10 @@ static int dispatch_core_bwd(int S, int dt_pad, CoreBwdParams& p, const void* xc
 
 }  // namespace mmb
 
-extern "C" int mmb_ss2d_core_bwd_tiles(int D) {
-    if (D <= 0) return MMB_ERR_INVALID_ARG;
-    return (D + 15) / 16;                  // upper bound: one dproj partial per 16-channel group (unused ones are zero)
+extern "C" int mmb_ss2d_core_bwd_tiles(int batch, int D) {
+    if (D <= 0 || batch < 0) return MMB_ERR_INVALID_ARG;
+    const int cw = 32 / mmb::core_bwd_split(batch > 0 ? batch : 1, D);       // channels per warp = per dproj partial
+    return (D + cw - 1) / cw;
 }
 
 extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float* dY, const float* Wdt,
@@ -439,11 +473,6 @@ extern "C" int mmb_ss2d_core_bwd(const void* xc, const float* proj, const float*
     p.T_row = g.T_row; p.NB_row = g.NB_row; p.nw = g.nw; p.T_col = g.T_col; p.NI_col = g.NI_col; p.NO_col = g.NO_col;
     p.cap = g.cap;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // partial rows of groups this launch does not own (S = 1 uses every other 16-channel slot) must read as zero
-    if (S == 1) {
-        cudaError_t e = cudaMemsetAsync(dproj_part, 0, sizeof(float) * (size_t)((D + 15) / 16) * batch * H * W * 4 * (32 + dt_pad), st);
-        if (e != cudaSuccess) return cuda_status(e);
-    }
     if (xc_dtype == MMB_F32) return dispatch_core_bwd<float>(S, dt_pad, p, xc, dY, proj, st);
     return dispatch_core_bwd<__nv_bfloat16>(S, dt_pad, p, xc, dY, proj, st);
 }

@@ -55,7 +55,10 @@ struct CoreFwdParams {
     int B, H, W, L, D, N, R, CT, tiles;
     int T_row, NB_row;                 // row view: NB_row blocks of T_row consecutive positions
     int nw, T_col, NI_col, NO_col;     // column view: NO_col column groups x NI_col row blocks
-    int cap;                           // steps a stage can hold
+    int cap;                           // steps a block can hold
+    int sub;                           // blocks per ring stage: 1, or 4 in the training forward, whose 8-step blocks (the
+                                       // checkpoint spacing the backward recomputes from) would otherwise cost a barrier
+                                       // round trip and a TMA issue per 8 steps (blocks shorter than 32 steps: up to -16 %)
     float* hsave;                      // NULL, or (B, 4, NBmax, D, 16): state after every block (training)
     int NBmax;
     int segs, bps_row, bps_col;        // L-parallel: segments per sequence, blocks per segment in either view
@@ -76,8 +79,8 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int XE = (int)sizeof(xc_t);
-    const int xbytes = p.cap * p.CT * XE, pbytes = p.cap * CP * 4;
-    const int xpad = (xbytes + 127) & ~127, ppad = (pbytes + 127) & ~127;
+    const int xsub = (p.cap * p.CT * XE + 127) & ~127, psub = (p.cap * CP * 4 + 127) & ~127;     // one block
+    const int xpad = p.sub * xsub, ppad = p.sub * psub;                                           // one ring stage
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kCoreStages * (xpad + ppad));
     uint64_t* empty = full + kCoreStages;
 
@@ -89,30 +92,34 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     const int seg = PASS == 0 ? 0 : blockIdx.x / p.tiles;
     const int c0 = tile * p.CT;
     const bool colview = (k & 1) != 0, rev = k >= 2;
-    const int NB = colview ? p.NO_col * p.NI_col : p.NB_row;
-    // blocks [jb0, jb1) of the sequence, in time order: the whole sequence, or this CTA's segment
-    int jb0 = 0, jb1 = NB;
+    const int NB = colview ? p.NO_col * p.NI_col : p.NB_row;        // blocks of the sequence
+    const int NST = (NB + p.sub - 1) / p.sub;                        // ring stages of the sequence (sub blocks each)
+    // stages [jb0, jb1) of the sequence, in time order: the whole sequence, or this CTA's segment (sub == 1 there)
+    int jb0 = 0, jb1 = NST;
     if (PASS != 0) {
         const int bps = colview ? p.bps_col : p.bps_row;
         jb0 = seg * bps;
         jb1 = jb0 + bps < NB ? jb0 + bps : NB;
     }
 
-    // Block jb (time order) -> TMA loads into stage (jb - jb0) % kCoreStages; issued by thread 0 only.
-    auto issue = [&](int jb) {
-        const int s = (jb - jb0) % kCoreStages;
-        const int blk = rev ? NB - 1 - jb : jb;
+    // Stage js (time order) -> TMA loads of its blocks into ring slot (js - jb0) % kCoreStages; issued by thread 0 only.
+    auto issue = [&](int js) {
+        const int s = (js - jb0) % kCoreStages;
+        const int nblk = min(p.sub, NB - js * p.sub);
         uint8_t* xs = smem_raw + s * (xpad + ppad);
         uint8_t* ps = xs + xpad;
-        if (!colview) {
-            mbar_expect_tx(&full[s], p.T_row * (p.CT * XE + CP * 4));
-            tma_load_3d(xs, &tmx_row, &full[s], c0, blk * p.T_row, b);
-            tma_load_4d(ps, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
-        } else {
-            const int o = blk / p.NI_col, i = blk % p.NI_col;
-            mbar_expect_tx(&full[s], p.nw * p.T_col * (p.CT * XE + CP * 4));
-            tma_load_4d(xs, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
-            tma_load_5d(ps, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
+        mbar_expect_tx(&full[s], nblk * (colview ? p.nw * p.T_col : p.T_row) * (p.CT * XE + CP * 4));
+        for (int sb = 0; sb < nblk; ++sb) {
+            const int jb = js * p.sub + sb;
+            const int blk = rev ? NB - 1 - jb : jb;
+            if (!colview) {
+                tma_load_3d(xs + sb * xsub, &tmx_row, &full[s], c0, blk * p.T_row, b);
+                tma_load_4d(ps + sb * psub, &tmp_row, &full[s], 0, k, blk * p.T_row, b);
+            } else {
+                const int o = blk / p.NI_col, i = blk % p.NI_col;
+                tma_load_4d(xs + sb * xsub, &tmx_col, &full[s], c0, o * p.nw, i * p.T_col, b);
+                tma_load_5d(ps + sb * psub, &tmp_col, &full[s], 0, k, o * p.nw, i * p.T_col, b);
+            }
         }
     };
 
@@ -186,16 +193,20 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         }
     }
 
-    for (int jb = jb0; jb < jb1; ++jb) {
-        const int jl = jb - jb0;
+    for (int js = jb0; js < jb1; ++js) {
+        const int jl = js - jb0;
         const int s = jl % kCoreStages, ph = (jl / kCoreStages) & 1;
-        // refill the stage block jb-1 has just left (inline producer: one thread)
-        if (tid == 0 && jb + kCoreStages - 1 < jb1) {
-            const int jn = jb + kCoreStages - 1;
+        // refill the ring slot stage js-1 has just left (inline producer: one thread)
+        if (tid == 0 && js + kCoreStages - 1 < jb1) {
+            const int jn = js + kCoreStages - 1;
             if (jl > 0) mbar_wait(&empty[(jn - jb0) % kCoreStages], ((jl - 1) / kCoreStages) & 1);
             issue(jn);
         }
         __syncwarp();
+        mbar_wait(&full[s], ph);
+      for (int sb = 0; sb < p.sub; ++sb) {
+        const int jb = js * p.sub + sb;
+        if (jb >= NB) break;
         const int blk = rev ? NB - 1 - jb : jb;
         // geometry: nrows x ncols positions, column-major in time; lane ti owns the slot / position
         // of the block's ti-th step in forward order (a block never has more than 32 steps)
@@ -215,9 +226,8 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             slot_l = hh * nwbox + ww;
             pos_l = pbase + hh * psh + ww;
         }
-        const xc_t* xs = reinterpret_cast<const xc_t*>(smem_raw + s * (xpad + ppad)) + cl;
-        const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad);
-        mbar_wait(&full[s], ph);
+        const xc_t* xs = reinterpret_cast<const xc_t*>(smem_raw + s * (xpad + ppad) + sb * xsub) + cl;
+        const float* ps = reinterpret_cast<const float*>(smem_raw + s * (xpad + ppad) + xpad + sb * psub);
 
         const bool single_col = nwbox == 1;     // slot / position are then affine in the step index: no shuffles
         // One group = four consecutive steps.  MODE 0: ragged last group of a block (per-step validity predicates);
@@ -355,6 +365,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             for (int j4 = 0; j4 < NS / 4; ++j4)
                 *reinterpret_cast<float4*>(hs + 4 * S * j4) = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
         }
+      }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -371,7 +382,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
 
 struct CorePlan {
     int S, CT, tiles, T_row, NB_row, nw, T_col, NI_col, NO_col, cap, threads;
-    int segs, bps_row, bps_col, ctas_per_sm;
+    int segs, bps_row, bps_col, ctas_per_sm, sub;
     size_t smem;
 };
 
@@ -455,13 +466,21 @@ static bool plan_core_blocks(int H, int W, int RP, int regs, int XE, bool train,
     if (cap > 32) cap = 32;
     if (cap < 8) cap = 8;
     cap = env_int("MMB_CORE_CAP", 4, 32, cap);
-    if (train) cap = kTrainCap;      // checkpoint spacing is part of the forward/backward contract
+    pl.sub = 1;
+    if (train) {                     // checkpoint spacing is part of the forward/backward contract: 8-step blocks, four per stage
+        cap = kTrainCap;
+        pl.sub = env_int("MMB_CORE_TRAIN_SUB", 1, 8, 4);
+    }
     CoreGeom g;
     if (!core_geometry(H, W, cap, g)) return false;
     pl.T_row = g.T_row; pl.NB_row = g.NB_row; pl.nw = g.nw; pl.T_col = g.T_col; pl.NI_col = g.NI_col; pl.NO_col = g.NO_col;
     pl.cap = g.cap;
     const size_t xpad = ((size_t)pl.cap * pl.CT * XE + 127) & ~(size_t)127, ppad = ((size_t)pl.cap * CP * 4 + 127) & ~(size_t)127;
-    pl.smem = kCoreStages * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
+    if (pl.sub > 1) {                // as many checkpoint blocks per stage as the stage budget of this occupancy holds
+        const int fit = (int)((size_t)stage_bytes / (xpad + ppad));
+        if (pl.sub > fit) pl.sub = fit < 1 ? 1 : fit;
+    }
+    pl.smem = kCoreStages * pl.sub * (xpad + ppad) + 2 * kCoreStages * sizeof(uint64_t);
     pl.ctas_per_sm = ctas;
     return pl.smem <= 200 * 1024;
 }
@@ -576,7 +595,7 @@ static int run_core(CorePlan& pl, CoreFwdParams& p, const void* xc, const float*
     if (pl.segs > 1 && ((int64_t)ws.total > workspace_bytes || !workspace)) return MMB_ERR_INVALID_ARG;
     if (train) { CoreGeom g; core_geometry(p.H, p.W, kTrainCap, g); p.NBmax = g.nblocks_max(); }
     p.T_row = pl.T_row; p.NB_row = pl.NB_row; p.nw = pl.nw; p.T_col = pl.T_col; p.NI_col = pl.NI_col; p.NO_col = pl.NO_col;
-    p.cap = pl.cap; p.CT = pl.CT; p.tiles = pl.tiles;
+    p.cap = pl.cap; p.CT = pl.CT; p.tiles = pl.tiles; p.sub = pl.sub;
     p.segs = pl.segs; p.bps_row = pl.bps_row; p.bps_col = pl.bps_col;
     uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
     p.seg_h = pl.segs > 1 ? reinterpret_cast<float*>(wsb + ws.seg_h) : nullptr;

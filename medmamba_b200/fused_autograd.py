@@ -126,7 +126,7 @@ def core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, d_state: int, dt_rank: in
     rp = ops.dt_pad(R)
     if proj.dtype != torch.float32 or dy.dtype != torch.float32 or xc.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("core_bwd: proj and dy must be float32, xc float32 or bfloat16")
-    tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(D))
+    tiles = lib().mmb_ss2d_core_bwd_tiles(_c_int(B), _c_int(D))
     dudir = torch.empty((B, H, W, 4, D), **f32)
     dproj_p = torch.empty((tiles, B, H, W, 4, 32 + rp), **f32)
     dA_p = torch.empty((B, 4 * D, N), **f32)

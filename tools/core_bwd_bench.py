@@ -24,7 +24,7 @@ Ds = torch.ones(4 * D, device="cuda")
 ydir, hsave = ops.ss2d_core(xc, proj, Wdt, bias, A, Ds, N, R, save_states=True)
 dY = torch.randn(B, H, W, D, device="cuda", generator=g)
 ci = ctypes.c_int
-tiles = lib().mmb_ss2d_core_bwd_tiles(ci(D))
+tiles = lib().mmb_ss2d_core_bwd_tiles(ci(B), ci(D))
 f32 = dict(dtype=torch.float32, device="cuda")
 dudir = torch.empty(B, H, W, 4, D, **f32); dproj = torch.empty(tiles, B, H, W, 4, 32 + rp, **f32)
 dA = torch.empty(B, 4 * D, N, **f32); dW = torch.empty(B, 4 * D, rp, **f32); dD = torch.empty(B, 4 * D, **f32); db = torch.empty(B, 4 * D, **f32)
