@@ -18,7 +18,7 @@ for r in rows:
         pass
 # the last forward pass: from the last patch-embed kernel onwards (bench runs warm-up steps first)
 names = [n for n, *_ in recs]
-starts = [i for i, n in enumerate(names) if "patch_embed_ln_kernel" in n]
+starts = [i for i, n in enumerate(names) if "patch_embed_ln" in n]
 lo = starts[-1] if starts else 0
 sel = recs[max(lo, 0):]
 agg = collections.defaultdict(lambda: [0, 0.0])
