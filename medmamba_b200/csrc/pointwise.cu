@@ -134,39 +134,50 @@ dwconv3x3_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* _
                 nb[dy][j] = __ldg(reinterpret_cast<const uint4*>(xb + ((int64_t)hy * W + wx) * x_pix));
             }
         }
+        // strips that touch no image border (most of them) skip the zero masks of the out-of-image taps
+        const bool interior = h >= 1 && h + 1 < H && w0 >= 1 && w0 + WS < W;
+        auto taps = [&](auto interior_tag) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const bool hok = (h + dy - 1 >= 0) && (h + dy - 1 < H);
-            float wk[3][8];
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const float4 w0v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c);
-                const float4 w1v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c + 4);
-                wk[dx][0] = w0v.x; wk[dx][1] = w0v.y; wk[dx][2] = w0v.z; wk[dx][3] = w0v.w;
-                wk[dx][4] = w1v.x; wk[dx][5] = w1v.y; wk[dx][6] = w1v.z; wk[dx][7] = w1v.w;
-            }
-#pragma unroll
-            for (int j = 0; j < WS + 2; ++j) {
-                const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
-                const uint32_t mk = ok ? 0xffffffffu : 0u;        // out-of-image taps: zero the packed words (4 ops, not 8)
-                const uint32_t wds[4] = {nb[dy][j].x & mk, nb[dy][j].y & mk, nb[dy][j].z & mk, nb[dy][j].w & mk};
-                float vv[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    // bf16 -> fp32 is a shift: low half is element 2e, high half element 2e + 1
-                    vv[2 * e] = __uint_as_float(wds[e] << 16);
-                    vv[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u);
-                }
+            for (int dy = 0; dy < 3; ++dy) {
+                const bool hok = INTERIOR || ((h + dy - 1 >= 0) && (h + dy - 1 < H));
+                float wk[3][8];
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const int i = j - dx;
-                    if (i >= 0 && i < WS) {
+                    const float4 w0v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c);
+                    const float4 w1v = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c + 4);
+                    wk[dx][0] = w0v.x; wk[dx][1] = w0v.y; wk[dx][2] = w0v.z; wk[dx][3] = w0v.w;
+                    wk[dx][4] = w1v.x; wk[dx][5] = w1v.y; wk[dx][6] = w1v.z; wk[dx][7] = w1v.w;
+                }
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(wk[dx][e], vv[e], acc[i][e]);
+                for (int j = 0; j < WS + 2; ++j) {
+                    uint32_t wds[4] = {nb[dy][j].x, nb[dy][j].y, nb[dy][j].z, nb[dy][j].w};
+                    if (!INTERIOR) {
+                        const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
+                        const uint32_t mk = ok ? 0xffffffffu : 0u;    // out-of-image taps: zero the packed words (4 ops, not 8)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) wds[e] &= mk;
+                    }
+                    float vv[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // bf16 -> fp32 is a shift: low half is element 2e, high half element 2e + 1
+                        vv[2 * e] = __uint_as_float(wds[e] << 16);
+                        vv[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int i = j - dx;
+                        if (i >= 0 && i < WS) {
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2)       // two channels per packed FFMA2
+                                fma2(acc[i][e], acc[i][e + 1], wk[dx][e], wk[dx][e + 1], vv[e], vv[e + 1], acc[i][e], acc[i][e + 1]);
+                        }
                     }
                 }
             }
-        }
+        };
+        if (interior) taps(std::true_type{}); else taps(std::false_type{});
 #pragma unroll
         for (int i = 0; i < WS; ++i) {
             const int wx = w0 + i;

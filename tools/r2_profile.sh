@@ -14,4 +14,13 @@ C5="python tools/core_bench.py --bf16 --batch 32 --res 512 --stage 0 --iters 1"
 timeout 300 $C5 > gpurun_out/r2p_c5_plain.log 2>&1 && timeout 900 $NCU -k regex:ss2d_core_fwd_kernel -s 6 -c 2 -o gpurun_out/r2p_core_fwd_lparallel_c5 $C5 > gpurun_out/r2p_ncu_c5.log 2>&1
 BW="python tools/core_bwd_bench.py --batch 128 --stage 0 --iters 1"
 timeout 300 $BW > gpurun_out/r2p_bwd_plain.log 2>&1 && timeout 900 $NCU -k regex:ss2d_core_bwd_kernel -s 2 -c 1 -o gpurun_out/r2p_core_bwd_stage1_b128 $BW > gpurun_out/r2p_ncu_bwd.log 2>&1
+# keep the box's gpurun_out small (64 MiB cap): text summaries of every capture, the .ncu-rep of the dominant kernel only
+for f in gpurun_out/r2p_*.ncu-rep; do
+  b=${f%.ncu-rep}
+  ncu -i $f --page raw --csv > ${b}_raw.csv 2>/dev/null && python tools/ncu_summary.py ${b}_raw.csv > ${b}_metrics.txt
+  ncu -i $f --page source --csv --print-source sass > ${b}_source.csv 2>/dev/null && python tools/ncu_opcodes.py ${b}_source.csv 30 > ${b}_opcodes.txt
+  rm -f ${b}_raw.csv ${b}_source.csv
+done
 ls -la gpurun_out/*.ncu-rep
+for f in gpurun_out/r2p_*.ncu-rep; do case $f in *core_fwd_stage1_b1024*) ;; *) rm -f $f;; esac; done
+du -sh gpurun_out
