@@ -176,7 +176,6 @@ class SelectiveScanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                 return_last_state=False):
-        # under no_grad nothing needs the checkpoints even if the inputs are leaves that require grad
         needs_grad = any(ctx.needs_input_grad)
         out, last, chunk_state = scan_forward(
             u, delta, A, B, C, D, z, delta_bias, delta_softplus,
@@ -206,4 +205,11 @@ class SelectiveScanFn(torch.autograd.Function):
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
     """See the module docstring; signature of mamba_ssm's ``selective_scan_fn`` (MedMamba.py:12)."""
+    tensors = (u, delta, A, B, C, D, z, delta_bias)
+    if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)):
+        # inference (also under no_grad with leaves that require grad: ctx.needs_input_grad does not see grad mode):
+        # no autograd node, no state checkpoints, the cp.async forward
+        out, last, _ = scan_forward(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                    want_last_state=return_last_state, want_chunk_state=False)
+        return (out, last) if return_last_state else out
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
