@@ -380,7 +380,7 @@ def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf
     gradient average as NCCL all-reduces over flat buckets launched from gradient hooks during backward."""
     torch.manual_seed(0)                                   # identical replicas
     net = mm.medmamba_t(NUM_CLASSES).to(dev).train()
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)      # train.py:192, one multi-tensor kernel
     red = mdist.GradAllReducer(net.parameters(), overlap=True)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(batch, 3, RES, RES, device=dev, generator=g)

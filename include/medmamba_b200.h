@@ -32,7 +32,7 @@ extern "C" {
 
 typedef enum { MMB_F32 = 0, MMB_BF16 = 1, MMB_F16 = 2 } mmb_dtype;
 
-#define MMB_ABI_VERSION 3
+#define MMB_ABI_VERSION 4
 
 /* ABI version of the loaded library (host only, no CUDA call). */
 int mmb_abi_version(void);
@@ -243,21 +243,26 @@ int mmb_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* d
                       int D, int64_t x_pixel_stride, float eps, int x_dtype, int dy_dtype, void* stream);
 
 /* Backward of mmb_outnorm_gate_fwd: dout (tokens, D) dense in z_dtype, ymerged from the forward ->
- *   dy (tokens, D) fp32, dz (tokens, D) dense in z_dtype,
+ *   dy (tokens, D) fp32, dz (tokens, D) in z_dtype with pixel stride dz_pixel_stride (D for a dense tensor; 2*D writes
+ *   it straight into the z half of the gradient of the in_proj output),
  *   dgb_part (mmb_partial_blocks(), 2, D) fp32: [.,0,:] dgamma, [.,1,:] dbeta partials. */
 int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, const void* z, const float* gamma,
                          const float* beta, float* dy, void* dz, float* dgb_part, int64_t tokens, int D,
-                         int64_t z_pixel_stride, float eps, int z_dtype, void* stream);
+                         int64_t z_pixel_stride, int64_t dz_pixel_stride, float eps, int z_dtype, void* stream);
 
-/* Backward of mmb_dwconv3x3_silu_fwd, step 1: ds = dxc * silu'(dwconv(x) + bias) (pre-activation recomputed),
+/* Backward of mmb_dwconv3x3_silu_fwd, step 1: ds = g * silu'(dwconv(x) + bias) (pre-activation recomputed), where the
+ * upstream gradient g of xc is the sum of the addends given (each may be NULL, not all): dxc (batch, H, W, D) fp32;
+ * dudir (batch, H, W, 4, D) fp32, the per-direction gradients of mmb_ss2d_core_bwd; dxc_extra (batch, H, W, D) dense in
+ * in_dtype, the x_proj GEMM's input gradient.  Folding the sum in here replaces a reduction, an add and a cast kernel.
  *   ds (batch, H, W, D) fp32, dwb_part (mmb_partial_blocks(), D, 10) fp32: [., c, 0..8] dweight taps, [., c, 9] dbias. */
 int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, const float* bias, const float* dxc,
-                              float* ds, float* dwb_part, int batch, int H, int W, int D,
-                              int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype, void* stream);
+                              const float* dudir, const void* dxc_extra, float* ds, float* dwb_part, int batch, int H,
+                              int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype, void* stream);
 
-/* ... step 2: dx = ds correlated with the flipped 3x3 kernel; dx (batch, H, W, D) dense in out_dtype. */
+/* ... step 2: dx = ds correlated with the flipped 3x3 kernel; dx (batch, H, W, D) in out_dtype with pixel stride
+ * dx_pixel_stride (D: dense; 2*D: the x half of the gradient of the in_proj output). */
 int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* dx, int batch, int H, int W, int D,
-                         int out_dtype, void* stream);
+                         int64_t dx_pixel_stride, int out_dtype, void* stream);
 
 /* Backward of mmb_shuffle_cat_residual_fwd w.r.t. the two branches (d inp = dout):
  *   dleft[..., j] = dout[..., 2j], dssm[..., j] = dout[..., 2j+1]; dense (tokens, c) in branch_dtype. */

@@ -15,7 +15,7 @@ from . import build as _build
 
 MMB_F32, MMB_BF16, MMB_F16 = 0, 1, 2
 _DTYPES = {torch.float32: MMB_F32, torch.bfloat16: MMB_BF16, torch.float16: MMB_F16}
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lock = threading.Lock()
 _lib = None

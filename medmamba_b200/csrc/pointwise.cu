@@ -16,7 +16,8 @@ namespace mmb {
 template <int WS, typename in_t, typename out_t, bool ACT = true, bool FLIP = false>
 __global__ void __launch_bounds__(256)
 dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-                      out_t* __restrict__ out, int B, int H, int W, int D, int64_t x_pix, int64_t x_batch) {
+                      out_t* __restrict__ out, int B, int H, int W, int D, int64_t x_pix, int64_t x_batch,
+                      int64_t o_pix) {
     // weights transposed into shared memory once per CTA: swt[tap][D], so a thread's 4 channels are one LDS.128
     extern __shared__ __align__(16) float swt[];
     for (int i = threadIdx.x; i < D * 9; i += blockDim.x) {
@@ -84,7 +85,7 @@ dwconv3x3_silu_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt,
                 float4 o;
                 if (ACT) { o.x = silu_f(acc[i][0]); o.y = silu_f(acc[i][1]); o.z = silu_f(acc[i][2]); o.w = silu_f(acc[i][3]); }
                 else { o.x = acc[i][0]; o.y = acc[i][1]; o.z = acc[i][2]; o.w = acc[i][3]; }
-                store4<out_t>(out + (((int64_t)b * H + h) * W + wx) * D + c, o);
+                store4<out_t>(out + (((int64_t)b * H + h) * W + wx) * o_pix + c, o);
             }
         }
     }
@@ -524,7 +525,7 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
     do {                                                                                                         \
         if (!aligned_for4<IN>(x) || !aligned_for4<OUT>(out)) return MMB_ERR_UNSUPPORTED;                         \
         dwconv3x3_silu_kernel<WS, IN, OUT><<<grid, 256, (size_t)D * 36, st>>>(reinterpret_cast<const IN*>(x), weight, bias,   \
-            reinterpret_cast<OUT*>(out), batch, H, W, D, x_pixel_stride, x_batch_stride);                        \
+            reinterpret_cast<OUT*>(out), batch, H, W, D, x_pixel_stride, x_batch_stride, (int64_t)D);                        \
         return launch_status();                                                                                  \
     } while (0)
     if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16 && D % 8 == 0 && x_pixel_stride % 8 == 0 && x_batch_stride % 8 == 0 &&
@@ -546,11 +547,12 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
 }
 
 extern "C" int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* dx, int batch, int H, int W, int D,
-                                    int out_dtype, void* stream) {
+                                    int64_t dx_pixel_stride, int out_dtype, void* stream) {
     using namespace mmb;
     if (!ds || !weight || !dx) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
     if (D % 4 != 0 || D > 1280 || !aligned_for4<float>(ds)) return MMB_ERR_UNSUPPORTED;
+    if (dx_pixel_stride < D || dx_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
     if (batch == 0) return MMB_OK;
     constexpr int WS = 4;
     const int64_t items = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 4);
@@ -560,13 +562,14 @@ extern "C" int mmb_dwconv3x3_bwd_dx(const float* ds, const float* weight, void* 
     if (out_dtype == MMB_F32) {
         if (!aligned_for4<float>(dx)) return MMB_ERR_UNSUPPORTED;
         dwconv3x3_silu_kernel<WS, float, float, false, true><<<grid, 256, (size_t)D * 36, st>>>(
-            ds, weight, nullptr, reinterpret_cast<float*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
+            ds, weight, nullptr, reinterpret_cast<float*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D, dx_pixel_stride);
         return launch_status();
     }
     if (out_dtype == MMB_BF16) {
         if (!aligned_for4<__nv_bfloat16>(dx)) return MMB_ERR_UNSUPPORTED;
         dwconv3x3_silu_kernel<WS, float, __nv_bfloat16, false, true><<<grid, 256, (size_t)D * 36, st>>>(
-            ds, weight, nullptr, reinterpret_cast<__nv_bfloat16*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D);
+            ds, weight, nullptr, reinterpret_cast<__nv_bfloat16*>(dx), batch, H, W, D, (int64_t)D, (int64_t)H * W * D,
+            dx_pixel_stride);
         return launch_status();
     }
     return MMB_ERR_UNSUPPORTED;

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256)
 outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ ymerged, const z_t* __restrict__ z,
                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dy,
                         z_t* __restrict__ dz, float* __restrict__ part, int64_t tokens, int D, int64_t z_pix,
-                        float eps) {
+                        int64_t dz_pix, float eps) {
     __shared__ float4 sred[8][2][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
@@ -72,7 +72,7 @@ outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ 
                     tt[e] = dn * gg[e];
                     m1 += tt[e]; m2 = fmaf(tt[e], xh[e], m2);
                 }
-                store4<z_t>(dz + tok * D + 4 * c4, make_float4(dzz[0], dzz[1], dzz[2], dzz[3]));
+                store4<z_t>(dz + tok * dz_pix + 4 * c4, make_float4(dzz[0], dzz[1], dzz[2], dzz[3]));
                 dg[i].x += dgg[0]; dg[i].y += dgg[1]; dg[i].z += dgg[2]; dg[i].w += dgg[3];
                 db[i].x += dbb[0]; db[i].y += dbb[1]; db[i].z += dbb[2]; db[i].w += dbb[3];
                 t[i] = make_float4(tt[0], tt[1], tt[2], tt[3]);
@@ -209,10 +209,14 @@ layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, con
 // xc = silu(s), s = dwconv(x) + bias.  K1: ds = dxc * silu'(s) (s recomputed), with per-CTA partials of
 // dweight (D, 9) and dbias (D).  The input gradient is then the flipped-kernel convolution of ds
 // (dwconv3x3_silu_kernel<..., ACT=false, FLIP=true> in pointwise.cu).
+// The upstream gradient is the sum of up to three addends, added here instead of by a chain of elementwise kernels:
+// dxc (tokens, D) fp32, the four direction slices of the core backward's dudir (tokens, 4, D) fp32, and the x_proj
+// GEMM's input gradient dxe (tokens, D) in the activation dtype.
 template <typename in_t>
 __global__ void __launch_bounds__(256)
 dwconv3x3_silu_bwd_ds_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-                             const float* __restrict__ dxc, float* __restrict__ ds, float* __restrict__ part,
+                             const float* __restrict__ dxc, const float* __restrict__ dudir, const in_t* __restrict__ dxe,
+                             float* __restrict__ ds, float* __restrict__ part,
                              int B, int H, int W, int D, int64_t x_pix, int64_t x_batch) {
     extern __shared__ float sacc[];              // [ty][C4][40]
     const int C4 = D / 4;
@@ -254,7 +258,18 @@ dwconv3x3_silu_bwd_ds_kernel(const in_t* __restrict__ x, const float* __restrict
 #pragma unroll
                 for (int e = 0; e < 4; ++e) s[e] = fmaf(wk[tp][e], xn[tp][e], s[e]);
             }
-            const float4 g = __ldg(reinterpret_cast<const float4*>(dxc + pix * D + c));
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dxc) g = __ldg(reinterpret_cast<const float4*>(dxc + pix * D + c));
+            if (dudir) {
+                const float4* dd = reinterpret_cast<const float4*>(dudir + pix * 4 * D + c);
+                const float4 a0 = __ldg(dd), a1 = __ldg(dd + C4), a2 = __ldg(dd + 2 * C4), a3 = __ldg(dd + 3 * C4);
+                g.x += (a0.x + a1.x) + (a2.x + a3.x); g.y += (a0.y + a1.y) + (a2.y + a3.y);
+                g.z += (a0.z + a1.z) + (a2.z + a3.z); g.w += (a0.w + a1.w) + (a2.w + a3.w);
+            }
+            if (dxe) {
+                const float4 e4 = load4<in_t>(dxe + pix * D + c);
+                g.x += e4.x; g.y += e4.y; g.z += e4.z; g.w += e4.w;
+            }
             const float gg[4] = {g.x, g.y, g.z, g.w};
             float d[4];
 #pragma unroll
@@ -306,11 +321,11 @@ extern "C" int mmb_partial_blocks(void) { return mmb::kPartBlocks; }
 
 extern "C" int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, const void* z, const float* gamma,
                                     const float* beta, float* dy, void* dz, float* dgb_part, int64_t tokens, int D,
-                                    int64_t z_pixel_stride, float eps, int z_dtype, void* stream) {
+                                    int64_t z_pixel_stride, int64_t dz_pixel_stride, float eps, int z_dtype, void* stream) {
     using namespace mmb;
     if (!dout || !ymerged || !z || !gamma || !beta || !dy || !dz || !dgb_part) return MMB_ERR_INVALID_ARG;
     if (tokens < 0 || D <= 0) return MMB_ERR_INVALID_ARG;
-    if (D % 4 != 0 || D > 1024 || z_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if (D % 4 != 0 || D > 1024 || z_pixel_stride % 4 != 0 || dz_pixel_stride % 4 != 0 || dz_pixel_stride < D) return MMB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(ymerged) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
          reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dgb_part)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -319,7 +334,7 @@ extern "C" int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, cons
         if (!al4<T>(z) || !al4<T>(dout) || !al4<T>(dz)) return MMB_ERR_UNSUPPORTED;                              \
         outnorm_gate_bwd_kernel<V, T><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const T*>(dout), ymerged,    \
             reinterpret_cast<const T*>(z), gamma, beta, dy, reinterpret_cast<T*>(dz), dgb_part, tokens, D,       \
-            z_pixel_stride, eps);                                                                                \
+            z_pixel_stride, dz_pixel_stride, eps);                                                               \
         return launch_status();                                                                                  \
     } while (0)
 #define MMB_OB_V(T)                                                                                              \
@@ -369,13 +384,15 @@ extern "C" int mmb_layernorm_bwd(const void* x, const void* dy, const float* gam
 }
 
 extern "C" int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, const float* bias, const float* dxc,
-                                         float* ds, float* dwb_part, int batch, int H, int W, int D,
-                                         int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype, void* stream) {
+                                         const float* dudir, const void* dxc_extra, float* ds, float* dwb_part, int batch,
+                                         int H, int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype,
+                                         void* stream) {
     using namespace mmb;
-    if (!x || !weight || !dxc || !ds || !dwb_part) return MMB_ERR_INVALID_ARG;
+    if (!x || !weight || (!dxc && !dudir && !dxc_extra) || !ds || !dwb_part) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
     if (D % 4 != 0 || D / 4 > 256 || x_pixel_stride % 4 != 0 || x_batch_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(dxc) | reinterpret_cast<uintptr_t>(ds) | reinterpret_cast<uintptr_t>(bias)) % 16 != 0)
+    if ((reinterpret_cast<uintptr_t>(dxc) | reinterpret_cast<uintptr_t>(ds) | reinterpret_cast<uintptr_t>(bias) |
+         reinterpret_cast<uintptr_t>(dudir) | reinterpret_cast<uintptr_t>(dxc_extra)) % 16 != 0)
         return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int C4 = D / 4;
@@ -387,7 +404,8 @@ extern "C" int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, con
         if (!al4<T>(x)) return MMB_ERR_UNSUPPORTED;                                                              \
         auto kern = dwconv3x3_silu_bwd_ds_kernel<T>;                                                             \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);\
-        kern<<<kPartBlocks, threads, smem, st>>>(reinterpret_cast<const T*>(x), weight, bias, dxc, ds, dwb_part, \
+        kern<<<kPartBlocks, threads, smem, st>>>(reinterpret_cast<const T*>(x), weight, bias, dxc, dudir,        \
+                                                 reinterpret_cast<const T*>(dxc_extra), ds, dwb_part,            \
                                                  batch, H, W, D, x_pixel_stride, x_batch_stride);                \
         return launch_status();                                                                                  \
     } while (0)

@@ -39,14 +39,14 @@ class DwConvSiluFn(torch.autograd.Function):
         part = torch.empty((_partial_blocks(), D, 10), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             with timed_launch("dwconv3x3_silu_bwd_ds", f"B={B},L={H * W},D={D}"):
-                st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), ptr(g), ptr(ds), ptr(part), _c_int(B),
-                                                     _c_int(H), _c_int(W), _c_int(D), i64(px), i64(bs),
+                st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), ptr(g), None, None, ptr(ds), ptr(part),
+                                                     _c_int(B), _c_int(H), _c_int(W), _c_int(D), i64(px), i64(bs),
                                                      _c_int(dtype_code(xv)), stream_ptr(dev))
             check(st, "mmb_dwconv3x3_silu_bwd_ds")
             dx = torch.empty((B, H, W, D), dtype=x.dtype, device=dev)
             with timed_launch("dwconv3x3_bwd_dx", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_dwconv3x3_bwd_dx(ptr(ds), ptr(w), ptr(dx), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
-                                                _c_int(dtype_code(dx)), stream_ptr(dev))
+                                                i64(D), _c_int(dtype_code(dx)), stream_ptr(dev))
             check(st, "mmb_dwconv3x3_bwd_dx")
         tot = part.sum(0)                                   # (D, 10)
         dw = tot[:, :9].reshape(D, 1, 3, 3).to(weight.dtype)
@@ -104,7 +104,7 @@ class CoreNormGateFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             with timed_launch("outnorm_gate_bwd", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_outnorm_gate_bwd(ptr(dout), ptr(merged), ptr(zv), ptr(g32), ptr(b32), ptr(dy), ptr(dz),
-                                                ptr(gb_part), i64(B * H * W), _c_int(D), i64(z_px), ctypes.c_float(eps),
+                                                ptr(gb_part), i64(B * H * W), _c_int(D), i64(z_px), i64(D), ctypes.c_float(eps),
                                                 _c_int(dtype_code(zv)), stream_ptr(dev))
             check(st, "mmb_outnorm_gate_bwd")
         dudir, dproj, dA, dWdt, dD, db = core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, N, R)
@@ -143,9 +143,110 @@ def core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, d_state: int, dt_rank: in
     return (dudir, dproj, dA_p.sum(0), dW_p.sum(0)[:, :R].reshape(4, D, R), dD_p.sum(0), db_p.sum(0).view(4, D))
 
 
+class SS2DInnerFn(torch.autograd.Function):
+    """Everything between in_proj and out_proj (MedMamba.py:292-301) as ONE autograd node, so that the backward's glue
+    runs inside the kernels instead of as elementwise launches: the gradient of xc -- four direction slices from the
+    core backward plus the x_proj GEMM's input gradient -- is summed by the dwconv backward kernel as it reads it, and
+    dx / dz are written straight into the two halves of d(xz).  (As separate nodes autograd needed, per block: a
+    reduction over the direction axis, an accumulate-add, a cast, two zero-filled (B, H, W, 2D) buffers, two slice
+    copies and an add: ~2 GB of traffic at stage 1, batch 128.)"""
+
+    @staticmethod
+    def forward(ctx, xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
+                eps, d_state, dt_rank):
+        B, H, W, D2 = xz.shape
+        D = D2 // 2
+        x, z = xz[..., :D], xz[..., D:]
+        bf16 = xz.dtype == torch.bfloat16 and D % 8 == 0
+        w_packed = ops.pack_x_proj(x_proj_weight.detach().float(), d_state, dt_rank)
+        xc = ops.dwconv3x3_silu(x, conv_w, conv_b, out_dtype=torch.bfloat16 if bf16 else torch.float32)
+        with torch.autocast("cuda", enabled=False):
+            if bf16:
+                wb = w_packed.to(torch.bfloat16)
+                proj = torch.mm(xc.view(-1, D), wb.t(), out_dtype=torch.float32).view(B, H, W, 4, -1)
+            else:
+                wb = w_packed
+                proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
+        A = -torch.exp(A_logs.detach().float())
+        Wdt_c, b_c, A_c, D_c = (dt_projs_weight.detach().float().contiguous(), dt_projs_bias.detach().float().contiguous(),
+                                A.contiguous(), Ds.detach().float().contiguous())
+        ydir, hsave = ops.ss2d_core(xc, proj, Wdt_c, b_c, A_c, D_c, d_state, dt_rank, save_states=True)
+        y, merged = ops.outnorm_gate(ydir, z, norm_w, norm_b, eps, want_merged=True, xc=xc, Ds=D_c)
+        ctx.save_for_backward(xz, conv_w, conv_b, xc, proj, wb, Wdt_c, b_c, A_c, D_c, norm_w, norm_b, merged, hsave)
+        ctx.meta = (eps, d_state, dt_rank, x_proj_weight.dtype, dt_projs_weight.dtype, dt_projs_bias.dtype, A_logs.dtype,
+                    Ds.dtype, x_proj_weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        xz, conv_w, conv_b, xc, proj, wb, Wdt, dt_bias, A, Ds, gamma, beta, merged, hsave = ctx.saved_tensors
+        eps, N, R, xw_t, wdt_t, b_t, alog_t, d_t, xw_shape = ctx.meta
+        B, H, W, D2 = xz.shape
+        D = D2 // 2
+        dev = xz.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        rp = ops.dt_pad(R)
+        x, z = xz[..., :D], xz[..., D:]
+        xv, x_px, x_bs = ops._token_view(x, uniform_batch=False)
+        zv, z_px, _ = ops._token_view(z)
+        dout = dout.to(zv.dtype).contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        dxz = torch.empty((B, H, W, D2), dtype=xz.dtype, device=dev)          # [..., :D] = dx, [..., D:] = dz
+        dy = torch.empty((B, H, W, D), **f32)
+        gb_part = torch.empty((_partial_blocks(), 2, D), **f32)
+        with torch.cuda.device(dev):
+            with timed_launch("outnorm_gate_bwd", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_outnorm_gate_bwd(ptr(dout), ptr(merged), ptr(zv), ptr(g32), ptr(b32), ptr(dy),
+                                                ctypes.c_void_p(dxz.data_ptr() + D * dxz.element_size()), ptr(gb_part),
+                                                i64(B * H * W), _c_int(D), i64(z_px), i64(D2), ctypes.c_float(eps),
+                                                _c_int(dtype_code(zv)), stream_ptr(dev))
+            check(st, "mmb_outnorm_gate_bwd")
+        dudir, dproj, dA, dWdt, dD, db = core_bwd(xc, proj, dy, Wdt, dt_bias, A, Ds, hsave, N, R)
+        # x_proj backward: two GEMMs (tensor cores in the autocast layout)
+        dproj2 = dproj.view(B * H * W, -1)
+        with torch.autocast("cuda", enabled=False):
+            if xc.dtype == torch.bfloat16:
+                gb16 = dproj2.to(torch.bfloat16)
+                dxe = torch.mm(gb16, wb)                                                      # (BL, D) bf16
+                dwp = torch.mm(gb16.t(), xc.view(-1, D), out_dtype=torch.float32)
+            else:
+                dxe = dproj2 @ wb
+                dwp = dproj2.t() @ xc.view(-1, D)
+        if dxe.dtype != xv.dtype:
+            dxe = dxe.to(xv.dtype)                                 # the kernel reads it in the dtype of x
+        # un-pack d Wpacked (4 * CP, D) -> d x_proj_weight (4, R + 2N, D): rows [B_n | C_n | dt_r] per direction
+        dwp = dwp.view(4, 32 + rp, D)
+        dxw = torch.cat((dwp[:, 32:32 + R], dwp[:, 0:N], dwp[:, 16:16 + N]), dim=1)
+        w = conv_w.detach().float().contiguous()
+        bb = conv_b.detach().float().contiguous() if conv_b is not None else None
+        ds = torch.empty((B, H, W, D), **f32)
+        part = torch.empty((_partial_blocks(), D, 10), **f32)
+        with torch.cuda.device(dev):
+            with timed_launch("dwconv3x3_silu_bwd_ds", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), None, ptr(dudir), ptr(dxe), ptr(ds), ptr(part),
+                                                     _c_int(B), _c_int(H), _c_int(W), _c_int(D), i64(x_px), i64(x_bs),
+                                                     _c_int(dtype_code(xv)), stream_ptr(dev))
+            check(st, "mmb_dwconv3x3_silu_bwd_ds")
+            with timed_launch("dwconv3x3_bwd_dx", f"B={B},L={H * W},D={D}"):
+                st = lib().mmb_dwconv3x3_bwd_dx(ptr(ds), ptr(w), ptr(dxz), _c_int(B), _c_int(H), _c_int(W), _c_int(D),
+                                                i64(D2), _c_int(dtype_code(dxz)), stream_ptr(dev))
+            check(st, "mmb_dwconv3x3_bwd_dx")
+        tot = part.sum(0)
+        dcw = tot[:, :9].reshape(D, 1, 3, 3).to(conv_w.dtype)
+        dcb = tot[:, 9].to(conv_b.dtype) if conv_b is not None else None
+        gb = gb_part.sum(0)
+        dAlog = (dA * A).to(alog_t)                                   # A = -exp(A_logs): dA/dA_logs = A
+        return (dxz, dcw, dcb, dxw.to(xw_t), dWdt.to(wdt_t), db.to(b_t), dAlog, dD.to(d_t), gb[0].to(gamma.dtype),
+                gb[1].to(beta.dtype), None, None, None)
+
+
 def ss2d_inner_train(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
                      eps, d_state, dt_rank):
     """Differentiable twin of ops.ss2d_inner (same kernels forward, hand-written kernels backward)."""
+    import os
+    if os.environ.get("MMB_TRAIN_FUSED_NODE", "1") != "0" and d_state <= 16:
+        return SS2DInnerFn.apply(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w,
+                                 norm_b, eps, d_state, dt_rank)
     B, H, W, D2 = xz.shape
     D = D2 // 2
     x, z = xz[..., :D], xz[..., D:]

@@ -21,10 +21,13 @@ import torch
 
 
 def build_optimizer(net: torch.nn.Module, lr: float = 1e-4, npz_dataset: bool = False) -> torch.optim.Optimizer:
-    """AdamW as train.py:189-192 builds it: library defaults for the .npz datasets, weight decay 1e-4 otherwise."""
+    """AdamW as train.py:189-192 builds it: library defaults for the .npz datasets, weight decay 1e-4 otherwise.
+    On CUDA parameters the fused multi-tensor implementation of the same update (one kernel per step instead of a
+    dozen foreach kernels); its state_dict has the reference's layout, so checkpoints stay interchangeable."""
+    fused = all(p.is_cuda for p in net.parameters())
     if npz_dataset:
-        return torch.optim.AdamW(net.parameters(), lr=lr)
-    return torch.optim.AdamW(net.parameters(), lr=lr, betas=(0.9, 0.999), weight_decay=1e-4)
+        return torch.optim.AdamW(net.parameters(), lr=lr, fused=fused)
+    return torch.optim.AdamW(net.parameters(), lr=lr, betas=(0.9, 0.999), weight_decay=1e-4, fused=fused)
 
 
 def build_scheduler(optimizer, milestones: Optional[Sequence[int]]):

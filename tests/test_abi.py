@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 def test_host_only_entry_points():
     from medmamba_b200 import _lib
     h = _lib.lib()
-    assert h.mmb_abi_version() == _lib.ABI_VERSION == 3
+    assert h.mmb_abi_version() == _lib.ABI_VERSION == 4
     h.mmb_source_digest.restype = ctypes.c_char_p
     from medmamba_b200 import build
     assert h.mmb_source_digest().decode() == build._digest()
