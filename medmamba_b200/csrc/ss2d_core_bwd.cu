@@ -210,6 +210,7 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             stp[(tl * 3 + 1) * 32] = ok ? sg : 0.f;
             stp[(tl * 3 + 2) * 32] = ok ? to_f<xc_t>(xs[sl * p.CT]) : 0.f;
         }
+        float h[NS];
         // one forward step of all 16 states; `park` stores h_{t-1} into history slab `hslot`
         auto advance = [&](float (&h)[NS], const int tl, const bool park, const int hslot) {
             const float4* bp = reinterpret_cast<const float4*>(ps + slot_of(tl) * CP) + q * (NS / 4);
@@ -256,18 +257,18 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
                 for (int e = 0; e < 4; ++e) { hp[e] = hist[(hslot * NS + j + e) * 32]; a[e] = ex2_approx(x[e]); }
 #pragma unroll
                 for (int e = 0; e < 4; e += 2) {
-                    float w0, w1, ht0, ht1, gt0, gt1, hpa0, hpa1, vb0, vb1, vc0, vc1, t0, t1, ga0, ga1;
-                    mul2(w0, w1, dlu, dlu, bb[e], bb[e + 1]);
-                    fma2(ht0, ht1, a[e], a[e + 1], hp[e], hp[e + 1], w0, w1);                  // h_t
+                    // h_t is not recomputed: it is the h_{t-1} the previous reverse iteration (step t+1) loaded, or the
+                    // state the forward re-run ended in (h); a g h_{t-1} is formed from the carried a g
+                    float gt0, gt1, vb0, vb1, vc0, vc1, t0, t1, ga0, ga1;
                     fma2(gt0, gt1, dy, dy, cc[e], cc[e + 1], gcar[j + e], gcar[j + e + 1]);    // g_t
-                    mul2(hpa0, hpa1, hp[e], hp[e + 1], a[e], a[e + 1]);
+                    mul2(ga0, ga1, a[e], a[e + 1], gt0, gt1);                                  // a_t g_t: carried to step t-1
                     mul2(vb0, vb1, gt0, gt1, dlu, dlu);                                        // dB_n of this channel
-                    mul2(vc0, vc1, dy, dy, ht0, ht1);                                          // dC_n of this channel
+                    mul2(vc0, vc1, dy, dy, h[j + e], h[j + e + 1]);                          // dC_n of this channel
                     fma2(adu[0], adu[1], gt0, gt1, bb[e], bb[e + 1], adu[0], adu[1]);          // sum_n g B
-                    mul2(t0, t1, gt0, gt1, hpa0, hpa1);                                        // g h_{t-1} a
+                    mul2(t0, t1, ga0, ga1, hp[e], hp[e + 1]);                                  // g h_{t-1} a
                     fma2(adA[0], adA[1], t0, t1, Ap[j + e], Ap[j + e + 1], adA[0], adA[1]);
                     fma2(dA[j + e], dA[j + e + 1], t0, t1, dli, dli, dA[j + e], dA[j + e + 1]);
-                    mul2(ga0, ga1, a[e], a[e + 1], gt0, gt1);
+                    h[j + e] = hp[e]; h[j + e + 1] = hp[e + 1];
                     gcar[j + e] = ok ? ga0 : gcar[j + e];
                     gcar[j + e + 1] = ok ? ga1 : gcar[j + e + 1];
                     // butterfly stages 1 (dB_n | dC_n over lane bit 4) and 2 (the two states of the pair over bit 3)
@@ -333,7 +334,6 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
             }
         };
 
-        float h[NS];
         __syncwarp();
         if (nsteps > kHalf) {
             // second half first: pass 1 over the first half, then phase A / B on steps kHalf .. TB-1

@@ -24,6 +24,30 @@ __global__ void k(float* out, int iters, float seed) {
                 a[i] = fmaf(e, a[i], b * 0.5f);
                 b = fmaf(a[i], 1e-6f, b);
             }
+        } else if (MODE == 4) {   // packed half exps: ex2.approx.f16x2 (two results per MUFU instruction?)
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                unsigned int* w = reinterpret_cast<unsigned int*>(&a[i]);
+                asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(*w));
+                w = reinterpret_cast<unsigned int*>(&a[i + 1]);
+                asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(*w));
+            }
+        } else if (MODE == 5) {   // ex2.approx.ftz.bf16x2
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                unsigned int* w = reinterpret_cast<unsigned int*>(&a[i]);
+                asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(*w));
+            }
+        } else if (MODE == 6) {   // f32 pair -> pack f16x2 -> ex2 -> unpack to f32 (what a scan step would do)
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                unsigned int w;
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(a[i + 1]), "f"(a[i]));
+                asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(w));
+                asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+                             : "=f"(a[i]), "=f"(a[i + 1]) : "r"(w));
+                a[i] -= 1.5f; a[i + 1] -= 1.5f;
+            }
         } else if (MODE == 3) {   // packed f32x2 fma
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -113,6 +137,9 @@ int main() {
         run<3>("ffma2", 16, w);
         run<1>("ex2", 16, w);
         run<2>("scanlike", 16, w);
+        run<4>("ex2.f16x2", 32, w);
+        run<5>("ex2.bf16x2", 32, w);
+        run<6>("pack+ex2h2+unpack", 16, w);
     }
     return 0;
 }
