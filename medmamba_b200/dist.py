@@ -87,6 +87,10 @@ class GradAllReducer:
         self.overlap = bool(overlap) and self.world > 1
         self._works = [None] * len(self.buckets)
         self._pending = [len(b) for b in self.buckets]
+        # Streams the hooks of a bucket ran on.  Autograd runs a backward node -- and the gradient accumulation that
+        # follows it -- on the stream of its forward; a model that forks a branch onto a side stream (SS_Conv_SSM's CNN
+        # branch) therefore finalises some gradients on that stream, and the pack kernel must wait for every one of them.
+        self._grad_streams = [set() for _ in self.buckets]
         self._hooks = []
         self.launched_in_backward = 0                       # buckets whose all-reduce started from a hook (last step)
         if self.overlap:
@@ -95,7 +99,9 @@ class GradAllReducer:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
 
     def _make_hook(self, bi: int):
-        def hook(_param):
+        def hook(param):
+            if param.is_cuda:
+                self._grad_streams[bi].add(torch.cuda.current_stream(param.device))
             self._pending[bi] -= 1
             if self._pending[bi] == 0 and self._works[bi] is None:
                 self._launch(bi)
@@ -104,6 +110,12 @@ class GradAllReducer:
 
     def _launch(self, bi: int) -> None:
         bucket, flat, views = self.buckets[bi], self.flat[bi], self.views[bi]
+        if flat.is_cuda and self._grad_streams[bi]:
+            cur = torch.cuda.current_stream(flat.device)
+            for st in self._grad_streams[bi]:
+                if st != cur:
+                    cur.wait_stream(st)
+            self._grad_streams[bi].clear()
         missing = [v for p, v in zip(bucket, views) if p.grad is None]
         if missing:
             torch._foreach_zero_(missing)

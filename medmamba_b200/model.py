@@ -15,6 +15,7 @@ hand-written sm_100a kernels behind the C ABI (``medmamba_b200.ops``).  The ``in
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable
 
 import torch
@@ -293,6 +294,16 @@ class SS_Conv_SSM(nn.Module):
                 x = torch.cudnn_convolution_relu(x, w, b, (1, 1), pad, (1, 1), 1)
         return x.permute(0, 2, 3, 1)
 
+    @staticmethod
+    def _dense_nchw_view(left: torch.Tensor) -> torch.Tensor:
+        """CNN branch input in NCHW *shape* with dense channels-last memory.  `left` is the first half of the channels
+        of the residual stream -- a strided view; permuted as it is, its strides are not dense, so BatchNorm takes ATen's
+        generic kernels and the autocast cast falls back to NCHW memory (layout-conversion kernels before every
+        convolution).  One small copy keeps the whole branch on the channels-last kernels."""
+        if left.is_cuda and os.environ.get("MMB_CNN_DENSE", "1") != "0":
+            left = left.contiguous()
+        return left.permute(0, 3, 1, 2)
+
     def _cnn_fast_ok(self, left: torch.Tensor) -> bool:
         return (getattr(self, "fast_cnn", True) and left.is_cuda and not self.training and left.shape[-1] % 4 == 0
                 and left.dtype in (torch.float32, torch.bfloat16) and ops.fused_available()
@@ -324,12 +335,26 @@ class SS_Conv_SSM(nn.Module):
             # side.wait_stream(main), so the pool cannot hand the block out again before that kernel has run
             # (record_stream's deferred frees made the allocator grow for several steps: cudaMalloc in the loop).
             return ops.shuffle_cat_residual(left, ssm, input)
+        if (self.training and input.is_cuda and torch.is_grad_enabled() and ops.train_branch_overlap_enabled()
+                and not torch.cuda.is_current_stream_capturing()):
+            # Training: the same fork / join around the CNN branch (cuDNN convolutions + BatchNorm).  Autograd runs every
+            # node's backward on the stream its forward ran on, so the branch's dgrad / wgrad / BatchNorm backward
+            # also leave the main stream and overlap the SS2D branch's backward (latency-bound, XU 29 % busy).
+            main = torch.cuda.current_stream(input.device)
+            side = ops.side_stream(input.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                left = self.conv33conv33conv11(self._dense_nchw_view(left)).permute(0, 2, 3, 1)
+            ssm = self.drop_path(self.self_attention(normed))
+            main.wait_stream(side)
+            if ops.shuffle_supported(ssm.shape[-1]) and ops.fused_available():
+                return ops.shuffle_cat_residual(left, ssm, input)
+            return channel_shuffle(torch.cat((left, ssm), dim=-1), groups=2) + input
         ssm = self.drop_path(self.self_attention(normed))
         if self._cnn_fast_ok(left):
             left = self._cnn_branch_fast(left)
         else:
-            # CNN branch in NCHW *shape*; the permuted view keeps channels-last strides for cuDNN
-            left = self.conv33conv33conv11(left.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+            left = self.conv33conv33conv11(self._dense_nchw_view(left)).permute(0, 2, 3, 1)
         if input.is_cuda and ops.shuffle_supported(ssm.shape[-1]) and ops.fused_available():
             return ops.shuffle_cat_residual(left, ssm, input)
         return channel_shuffle(torch.cat((left, ssm), dim=-1), groups=2) + input

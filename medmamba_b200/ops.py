@@ -36,6 +36,11 @@ def branch_overlap_enabled() -> bool:
     return os.environ.get("MMB_BRANCH_OVERLAP", "1") != "0"
 
 
+def train_branch_overlap_enabled() -> bool:
+    """In training the CNN branch of a block runs on the side stream too (MMB_TRAIN_BRANCH_OVERLAP=0 turns it off)."""
+    return os.environ.get("MMB_TRAIN_BRANCH_OVERLAP", "1") != "0"
+
+
 def fused_available() -> bool:
     """True when the CUDA library is loadable (it is built on demand; failure raises)."""
     lib()

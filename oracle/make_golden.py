@@ -144,6 +144,30 @@ def vssm_t_batch256(mod, ref_scan, n=256, chunk=8):
     return _np(dict(logits=torch.cat(outs), weight_seed=0, input_seed=2))
 
 
+SIZES = {   # the sizes train.py:179-182 / test.py:66-72 construct besides 'T'
+    "S": dict(depths=[2, 2, 8, 2], dims=[96, 192, 384, 768]),
+    "B": dict(depths=[2, 2, 12, 2], dims=[128, 256, 512, 1024]),
+    "else": dict(depths=[2, 3, 3, 2], dims=[96, 192, 384, 768]),
+}
+
+
+def vssm_sizes(mod, ref_scan, n=2):
+    """MedMamba-S, -B and the default-size branch (train.py:180-182): seed 0 weights, n randn images (seed 3), fp32, eval."""
+    mod.selective_scan_fn = ref_scan
+    rec = {}
+    for name, cfg in SIZES.items():
+        torch.manual_seed(0)
+        net = mod.VSSM(num_classes=6, **cfg).eval()
+        torch.manual_seed(3)
+        x = torch.randn(n, 3, 224, 224)
+        with torch.no_grad():
+            rec[f"{name}.logits"] = net(x)
+        rec[f"{name}.depths"], rec[f"{name}.dims"] = np.array(cfg["depths"]), np.array(cfg["dims"])
+        print(f"  size {name} done", flush=True)
+    rec.update(weight_seed=0, input_seed=3)
+    return _np(rec)
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
@@ -151,6 +175,9 @@ def main():
     ref_scan = iface.selective_scan_ref
     if "--b256" in sys.argv:          # ~6 minutes of CPU; kept apart from the quick fixtures
         np.savez_compressed(os.path.join(OUT, "vssm_t_b256.npz"), **vssm_t_batch256(mod, ref_scan))
+        return
+    if "--sizes" in sys.argv:         # ~1 minute of CPU
+        np.savez_compressed(os.path.join(OUT, "vssm_sizes.npz"), **vssm_sizes(mod, ref_scan))
         return
     np.savez_compressed(os.path.join(OUT, "scan_small.npz"), **scan_cases(ref_scan))
     np.savez_compressed(os.path.join(OUT, "index_maps.npz"), **index_cases(mod))

@@ -248,6 +248,34 @@ def test_vssm_t_config1_logits_and_top1():
     assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
 
 
+@pytest.mark.parametrize("size", ["S", "B", "else"])
+def test_vssm_other_sizes_logits_and_top1(size):
+    """The other three sizes the reference's drivers construct (train.py:180-182, test.py:68-72): MedMamba-S, MedMamba-B
+    (d_inner 128 .. 1024, dt_rank 4 .. 32: every dt padding the core kernel has) and the default [2, 3, 3, 2] -- fp32 and
+    bf16 autocast forward against logits of the unmodified reference (oracle/make_golden.py --sizes)."""
+    import medmamba_b200 as mm
+    g = _load("vssm_sizes.npz")
+    depths, dims = [int(v) for v in g[f"{size}.depths"]], [int(v) for v in g[f"{size}.dims"]]
+    want = g[f"{size}.logits"]
+    torch.manual_seed(int(g["weight_seed"]))
+    net = mm.VSSM(depths=depths, dims=dims, num_classes=6).cuda().eval()
+    torch.manual_seed(int(g["input_seed"]))
+    x = torch.randn(want.shape[0], 3, 224, 224).cuda()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            logits = net(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert_close(logits, want, 1e-3, 1e-4, f"MedMamba-{size} logits")
+    assert torch.equal(logits.argmax(1).cpu(), want.argmax(1))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        l16 = net(x).float().cpu()
+    rel = (l16 - want).abs().max().item() / want.abs().max().item()
+    assert torch.equal(l16.argmax(1), want.argmax(1)) and rel < 1e-2, rel
+
+
 def test_core_long_sequence_config5_stage1():
     """BASELINE config 5 (512x512 images): the stage-1 grid is 128x128, L = 16384 -- 512 ring blocks per row
     direction, one column block per 4 columns -- against the fp64 oracle, model-like magnitudes."""
