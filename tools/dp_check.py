@@ -20,6 +20,7 @@ def grads(overlap):
     out = []
     for _ in range(3):          # repeated: a race would not hit the same way every time
         net.zero_grad(set_to_none=True)
+        torch.manual_seed(1234)     # DropPath draws per step
         red.begin_step()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = torch.nn.functional.cross_entropy(net(x).float(), y)
