@@ -424,7 +424,8 @@ def train_record(mm, ops, mdist, dev, dist, rank, world, batch, steps, dtype="bf
            "global_batch": world * batch, "steps": steps, "ms_per_step": round(ms / steps, 3),
            "value": round(world * batch * steps / (ms / 1e3), 1), "unit": UNIT, "gpu_launches": timer.launches,
            "parallelism": f"dp{world}, {len(red.buckets)} flat fp32 buckets ({sum(f.numel() for f in red.flat) * 4 / 1e6:.1f} MB), "
-                          f"NCCL all-reduce launched from gradient hooks during backward",
+                          f"NCCL all-reduce launched from gradient hooks during backward; the CNN branch of every block "
+                          f"runs on a side stream, forward and (through autograd) backward",
            "allreduce": None if world == 1 else {
                "buckets": len(red.buckets), "buckets_launched_during_backward": fired,
                "ms_per_step_without_exchange": round(ms_noex / steps, 3),

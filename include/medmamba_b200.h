@@ -215,8 +215,9 @@ int mmb_patch_merge_ln_fwd(const void* x, const float* gamma, const float* beta,
  * as per-CTA / per-batch partials that the caller sums over the leading axis: no float atomics, results are
  * bit-reproducible. ---- */
 
-/* Rows of the partial buffers of mmb_outnorm_gate_bwd and mmb_dwconv3x3_silu_bwd_ds (host only). */
+/* Rows of the partial buffers of mmb_outnorm_gate_bwd / mmb_layernorm_bwd, and of mmb_dwconv3x3_silu_bwd_ds (host only). */
 int mmb_partial_blocks(void);
+int mmb_dwconv_partial_blocks(void);
 
 /* Channel groups (one per warp: 32 or 16 channels, by launch size) whose dproj partials mmb_ss2d_core_bwd writes for this
  * problem (host only): the leading extent of dproj_part.  Every partial row is written; nothing needs a memset. */
@@ -254,7 +255,7 @@ int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, const void* z, 
  * upstream gradient g of xc is the sum of the addends given (each may be NULL, not all): dxc (batch, H, W, D) fp32;
  * dudir (batch, H, W, 4, D) fp32, the per-direction gradients of mmb_ss2d_core_bwd; dxc_extra (batch, H, W, D) dense in
  * in_dtype, the x_proj GEMM's input gradient.  Folding the sum in here replaces a reduction, an add and a cast kernel.
- *   ds (batch, H, W, D) fp32, dwb_part (mmb_partial_blocks(), D, 10) fp32: [., c, 0..8] dweight taps, [., c, 9] dbias. */
+ *   ds (batch, H, W, D) fp32, dwb_part (mmb_dwconv_partial_blocks(), D, 10) fp32: [., c, 0..8] dweight taps, [., c, 9] dbias. */
 int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, const float* bias, const float* dxc,
                               const float* dudir, const void* dxc_extra, float* ds, float* dwb_part, int batch, int H,
                               int W, int D, int64_t x_pixel_stride, int64_t x_batch_stride, int in_dtype, void* stream);

@@ -4,63 +4,107 @@
 
 namespace mmb {
 
-constexpr int kPartBlocks = 296;     // CTAs of the reducing kernels = rows of their partial buffers (2 per SM)
+constexpr int kPartBlocks = 592;     // CTAs of the LayerNorm-type reducing kernels = rows of their partial buffers (4 per SM)
+constexpr int kConvPartBlocks = 296; // the same for dwconv3x3_silu_bwd_ds (128 registers, 40 KB of partials per CTA: 2 per SM;
+                                     // 592 CTAs ran 2.4x slower)
+
+// Per-CTA partial of two per-channel sums (dgamma / dbeta): every lane holds the sums of channel slot (gl + G i) over
+// the tokens it saw.  Warps are added in fixed order through shared memory, then the 32 / G token sub-groups of a
+// warp with xor-shuffles: bit-reproducible.  part: (gridDim.x, 2, D).
+template <int V, int G>
+__device__ __forceinline__ void store_gb_partial(const float4 (&dg)[V], const float4 (&db)[V], float* __restrict__ part, int D) {
+    __shared__ float4 sred[8][2][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % G;
+    const int C4 = D / 4;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        sred[wib][0][lane] = dg[i]; sred[wib][1][lane] = db[i];
+        __syncthreads();
+        if (wib < 2) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < 8; ++w) {
+                const float4 q4 = sred[w][wib][lane];
+                a.x += q4.x; a.y += q4.y; a.z += q4.z; a.w += q4.w;
+            }
+#pragma unroll
+            for (int off = G; off < 32; off <<= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, off); a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, off); a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+            }
+            const int c4 = gl + G * i;
+            if (lane < G && c4 < C4) reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * D)[c4] = a;
+        }
+        __syncthreads();
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // out = LayerNorm(y) * silu(z):  given dout -> dy (fp32), dz, and per-CTA partials of dgamma / dbeta.
-template <int V, typename z_t>
+// G lanes per token (all 32, or 16 / 8 for narrow rows), every global load of a token issued before the first
+// reduction: the first version (one warp per token, z / dout loaded after the statistics, 2 CTAs per SM) ran at a
+// sixth of the HBM roofline at batch 128.
+template <int V, typename z_t, int G>
 __global__ void __launch_bounds__(256)
 outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ ymerged, const z_t* __restrict__ z,
                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dy,
                         z_t* __restrict__ dz, float* __restrict__ part, int64_t tokens, int D, int64_t z_pix,
                         int64_t dz_pix, float eps) {
-    __shared__ float4 sred[8][2][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int TPW = 32 / G;
+    constexpr bool EARLY = V <= 4;      // wide rows (D > 512): z / dout loaded after the statistics, or 8 more float4 spill
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % G;
     const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
     const int C4 = D / 4;
+    const int64_t ngroups = (tokens + TPW - 1) / TPW;
     float4 g[V], bt[V], dg[V], db[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const int c4 = lane + 32 * i;
+        const int c4 = gl + G * i;
         g[i] = c4 < C4 ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         bt[i] = c4 < C4 ? __ldg(reinterpret_cast<const float4*>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i];
     }
-    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
-        float4 v[V];
+    for (int64_t grp = warp; grp < ngroups; grp += nwarps) {
+        const int64_t tok = grp * TPW + lane / G;
+        const bool tvalid = tok < tokens;
+        float4 v[V], zz[EARLY ? V : 1], go[EARLY ? V : 1];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            v[i] = c4 < C4 ? __ldg(reinterpret_cast<const float4*>(ymerged + tok * D) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c4 = gl + G * i;
+            const bool ok = tvalid && c4 < C4;
+            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(ymerged + tok * D) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EARLY) {
+                zz[i] = ok ? load4<z_t>(z + tok * z_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                go[i] = ok ? load4<z_t>(dout + tok * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        for (int off = G / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         const float mean = sum / (float)D;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (lane + 32 * i < C4) {
+            if (gl + G * i < C4) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
                 sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        for (int off = G / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
         const float rstd = rsqrtf(sq / (float)D + eps);
         float4 t[V];
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
+            const int c4 = gl + G * i;
             t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 < C4) {
-                const float4 zz = load4<z_t>(z + tok * z_pix + 4 * c4);
-                const float4 go = load4<z_t>(dout + tok * D + 4 * c4);
+            if (tvalid && c4 < C4) {
                 const float xh[4] = {v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd};
                 const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w}, bb[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
-                const float zq[4] = {zz.x, zz.y, zz.z, zz.w}, gq[4] = {go.x, go.y, go.z, go.w};
+                const float4 z4 = EARLY ? zz[EARLY ? i : 0] : load4<z_t>(z + tok * z_pix + 4 * c4);
+                const float4 g4 = EARLY ? go[EARLY ? i : 0] : load4<z_t>(dout + tok * D + 4 * c4);
+                const float zq[4] = {z4.x, z4.y, z4.z, z4.w}, gq[4] = {g4.x, g4.y, g4.z, g4.w};
                 float dzz[4], tt[4], dgg[4], dbb[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -80,15 +124,15 @@ outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ 
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = G / 2; off > 0; off >>= 1) {
             m1 += __shfl_xor_sync(0xffffffffu, m1, off);
             m2 += __shfl_xor_sync(0xffffffffu, m2, off);
         }
         m1 /= (float)D; m2 /= (float)D;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            if (c4 < C4) {
+            const int c4 = gl + G * i;
+            if (tvalid && c4 < C4) {
                 float4 o;
                 o.x = rstd * (t[i].x - m1 - v[i].x * m2); o.y = rstd * (t[i].y - m1 - v[i].y * m2);
                 o.z = rstd * (t[i].z - m1 - v[i].z * m2); o.w = rstd * (t[i].w - m1 - v[i].w * m2);
@@ -96,22 +140,7 @@ outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ 
             }
         }
     }
-    // per-CTA partial of dgamma / dbeta: warps added in fixed order
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-        sred[wib][0][lane] = dg[i]; sred[wib][1][lane] = db[i];
-        __syncthreads();
-        if (wib < 2) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int w = 0; w < 8; ++w) {
-                const float4 q4 = sred[w][wib][lane];
-                a.x += q4.x; a.y += q4.y; a.z += q4.z; a.w += q4.w;
-            }
-            const int c4 = lane + 32 * i;
-            if (c4 < C4) reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * D)[c4] = a;
-        }
-        __syncthreads();
-    }
+    store_gb_partial<V, G>(dg, db, part, D);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -119,49 +148,53 @@ outnorm_gate_bwd_kernel(const z_t* __restrict__ dout, const float* __restrict__ 
 // training.  Statistics are recomputed from x (the row is in registers anyway), so the forward saves nothing:
 //   xhat = (x - mean) rstd,  t = dy gamma,  dx = rstd (t - mean(t) - xhat mean(t xhat)),
 //   dgamma += dy xhat,  dbeta += dy   (per-CTA partials, warps added in fixed order: bit-reproducible).
-template <int V, typename x_t, typename dy_t>
+template <int V, typename x_t, typename dy_t, int G>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, const float* __restrict__ gamma,
                      x_t* __restrict__ dx, float* __restrict__ part, int64_t tokens, int D, int64_t x_pix, float eps) {
-    __shared__ float4 sred[8][2][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int TPW = 32 / G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % G;
     const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
     const int C4 = D / 4;
+    const int64_t ngroups = (tokens + TPW - 1) / TPW;
     float4 g[V], dg[V], db[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const int c4 = lane + 32 * i;
+        const int c4 = gl + G * i;
         g[i] = c4 < C4 ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i];
     }
-    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+    for (int64_t grp = warp; grp < ngroups; grp += nwarps) {
+        const int64_t tok = grp * TPW + lane / G;
+        const bool tvalid = tok < tokens;
         float4 v[V], t[V];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            v[i] = c4 < C4 ? load4<x_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            t[i] = c4 < C4 ? load4<dy_t>(dy + tok * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c4 = gl + G * i;
+            const bool ok = tvalid && c4 < C4;
+            v[i] = ok ? load4<x_t>(x + tok * x_pix + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[i] = ok ? load4<dy_t>(dy + tok * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        for (int off = G / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         const float mean = sum / (float)D;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (lane + 32 * i < C4) {
+            if (gl + G * i < C4) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
                 sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        for (int off = G / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
         const float rstd = rsqrtf(sq / (float)D + eps);
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (lane + 32 * i < C4) {
+            if (tvalid && gl + G * i < C4) {
                 v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
                 dg[i].x = fmaf(t[i].x, v[i].x, dg[i].x); dg[i].y = fmaf(t[i].y, v[i].y, dg[i].y);
                 dg[i].z = fmaf(t[i].z, v[i].z, dg[i].z); dg[i].w = fmaf(t[i].w, v[i].w, dg[i].w);
@@ -172,15 +205,15 @@ layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, con
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = G / 2; off > 0; off >>= 1) {
             m1 += __shfl_xor_sync(0xffffffffu, m1, off);
             m2 += __shfl_xor_sync(0xffffffffu, m2, off);
         }
         m1 /= (float)D; m2 /= (float)D;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c4 = lane + 32 * i;
-            if (c4 < C4) {
+            const int c4 = gl + G * i;
+            if (tvalid && c4 < C4) {
                 float4 o;
                 o.x = rstd * (t[i].x - m1 - v[i].x * m2); o.y = rstd * (t[i].y - m1 - v[i].y * m2);
                 o.z = rstd * (t[i].z - m1 - v[i].z * m2); o.w = rstd * (t[i].w - m1 - v[i].w * m2);
@@ -188,21 +221,7 @@ layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, con
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-        sred[wib][0][lane] = dg[i]; sred[wib][1][lane] = db[i];
-        __syncthreads();
-        if (wib < 2) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int w = 0; w < 8; ++w) {
-                const float4 q4 = sred[w][wib][lane];
-                a.x += q4.x; a.y += q4.y; a.z += q4.z; a.w += q4.w;
-            }
-            const int c4 = lane + 32 * i;
-            if (c4 < C4) reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * D)[c4] = a;
-        }
-        __syncthreads();
-    }
+    store_gb_partial<V, G>(dg, db, part, D);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -318,6 +337,7 @@ template <typename T> static bool al4(const void* p) { return reinterpret_cast<u
 }  // namespace mmb
 
 extern "C" int mmb_partial_blocks(void) { return mmb::kPartBlocks; }
+extern "C" int mmb_dwconv_partial_blocks(void) { return mmb::kConvPartBlocks; }
 
 extern "C" int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, const void* z, const float* gamma,
                                     const float* beta, float* dy, void* dz, float* dgb_part, int64_t tokens, int D,
@@ -329,20 +349,22 @@ extern "C" int mmb_outnorm_gate_bwd(const void* dout, const float* ymerged, cons
     if ((reinterpret_cast<uintptr_t>(ymerged) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
          reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dgb_part)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define MMB_OB(V, T)                                                                                             \
+#define MMB_OB(V, T, G)                                                                                          \
     do {                                                                                                         \
         if (!al4<T>(z) || !al4<T>(dout) || !al4<T>(dz)) return MMB_ERR_UNSUPPORTED;                              \
-        outnorm_gate_bwd_kernel<V, T><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const T*>(dout), ymerged,    \
+        outnorm_gate_bwd_kernel<V, T, G><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const T*>(dout), ymerged, \
             reinterpret_cast<const T*>(z), gamma, beta, dy, reinterpret_cast<T*>(dz), dgb_part, tokens, D,       \
             z_pixel_stride, dz_pixel_stride, eps);                                                               \
         return launch_status();                                                                                  \
     } while (0)
 #define MMB_OB_V(T)                                                                                              \
     do {                                                                                                         \
-        if (D <= 128) MMB_OB(1, T);                                                                              \
-        if (D <= 256) MMB_OB(2, T);                                                                              \
-        if (D <= 512) MMB_OB(4, T);                                                                              \
-        MMB_OB(8, T);                                                                                            \
+        if (D <= 32) MMB_OB(1, T, 8);                                                                            \
+        if (D <= 64) MMB_OB(1, T, 16);                                                                           \
+        if (D <= 128) MMB_OB(1, T, 32);                                                                          \
+        if (D <= 256) MMB_OB(2, T, 32);                                                                          \
+        if (D <= 512) MMB_OB(4, T, 32);                                                                          \
+        MMB_OB(8, T, 32);                                                                                        \
     } while (0)
     if (z_dtype == MMB_F32) MMB_OB_V(float);
     if (z_dtype == MMB_BF16) MMB_OB_V(__nv_bfloat16);
@@ -360,19 +382,21 @@ extern "C" int mmb_layernorm_bwd(const void* x, const void* dy, const float* gam
     if (D % 4 != 0 || D > 512 || x_pixel_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dgb_part)) % 16 != 0) return MMB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define MMB_LB(V, TX, TY)                                                                                        \
+#define MMB_LB(V, TX, TY, G)                                                                                     \
     do {                                                                                                         \
         if (!al4<TX>(x) || !al4<TX>(dx) || !al4<TY>(dy)) return MMB_ERR_UNSUPPORTED;                             \
-        layernorm_bwd_kernel<V, TX, TY><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const TX*>(x),             \
+        layernorm_bwd_kernel<V, TX, TY, G><<<kPartBlocks, 256, 0, st>>>(reinterpret_cast<const TX*>(x),          \
             reinterpret_cast<const TY*>(dy), gamma, reinterpret_cast<TX*>(dx), dgb_part, tokens, D,              \
             x_pixel_stride, eps);                                                                                \
         return launch_status();                                                                                  \
     } while (0)
 #define MMB_LB_V(TX, TY)                                                                                         \
     do {                                                                                                         \
-        if (D <= 128) MMB_LB(1, TX, TY);                                                                         \
-        if (D <= 256) MMB_LB(2, TX, TY);                                                                         \
-        MMB_LB(4, TX, TY);                                                                                       \
+        if (D <= 32) MMB_LB(1, TX, TY, 8);                                                                       \
+        if (D <= 64) MMB_LB(1, TX, TY, 16);                                                                      \
+        if (D <= 128) MMB_LB(1, TX, TY, 32);                                                                     \
+        if (D <= 256) MMB_LB(2, TX, TY, 32);                                                                     \
+        MMB_LB(4, TX, TY, 32);                                                                                   \
     } while (0)
     if (x_dtype == MMB_F32 && dy_dtype == MMB_F32) MMB_LB_V(float, float);
     if (x_dtype == MMB_F32 && dy_dtype == MMB_BF16) MMB_LB_V(float, __nv_bfloat16);
@@ -404,7 +428,7 @@ extern "C" int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, con
         if (!al4<T>(x)) return MMB_ERR_UNSUPPORTED;                                                              \
         auto kern = dwconv3x3_silu_bwd_ds_kernel<T>;                                                             \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);\
-        kern<<<kPartBlocks, threads, smem, st>>>(reinterpret_cast<const T*>(x), weight, bias, dxc, dudir,        \
+        kern<<<kConvPartBlocks, threads, smem, st>>>(reinterpret_cast<const T*>(x), weight, bias, dxc, dudir,    \
                                                  reinterpret_cast<const T*>(dxc_extra), ds, dwb_part,            \
                                                  batch, H, W, D, x_pixel_stride, x_batch_stride);                \
         return launch_status();                                                                                  \

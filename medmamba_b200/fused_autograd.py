@@ -17,6 +17,10 @@ def _partial_blocks() -> int:
     return lib().mmb_partial_blocks()
 
 
+def _conv_partial_blocks() -> int:
+    return lib().mmb_dwconv_partial_blocks()
+
+
 class DwConvSiluFn(torch.autograd.Function):
     """xc = silu(dwconv3x3(x) + bias), channels-last (MedMamba.py:294-295)."""
 
@@ -36,7 +40,7 @@ class DwConvSiluFn(torch.autograd.Function):
         bb = bias.detach().float().contiguous() if bias is not None else None
         g = dxc.float().contiguous()
         ds = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
-        part = torch.empty((_partial_blocks(), D, 10), dtype=torch.float32, device=dev)
+        part = torch.empty((_conv_partial_blocks(), D, 10), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             with timed_launch("dwconv3x3_silu_bwd_ds", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), ptr(g), None, None, ptr(ds), ptr(part),
@@ -220,7 +224,7 @@ class SS2DInnerFn(torch.autograd.Function):
         w = conv_w.detach().float().contiguous()
         bb = conv_b.detach().float().contiguous() if conv_b is not None else None
         ds = torch.empty((B, H, W, D), **f32)
-        part = torch.empty((_partial_blocks(), D, 10), **f32)
+        part = torch.empty((_conv_partial_blocks(), D, 10), **f32)
         with torch.cuda.device(dev):
             with timed_launch("dwconv3x3_silu_bwd_ds", f"B={B},L={H * W},D={D}"):
                 st = lib().mmb_dwconv3x3_silu_bwd_ds(ptr(xv), ptr(w), ptr(bb), None, ptr(dudir), ptr(dxe), ptr(ds), ptr(part),
