@@ -160,70 +160,128 @@ __global__ void __launch_bounds__(128) scan_bwd_kernel(const ScanBwdParams p) {
         }
         __syncthreads();
 
+        // Both phases walk the chunk four steps at a time: one LDS.128 per row tile (u, delta, dy, d softplus) and per state
+        // (B_n, C_n) serves four steps, the state history is one float4 per (step, thread), and the per-state arithmetic runs
+        // as packed FMUL2 / FFMA2 pairs.  Steps beyond the sequence have delta = 0, dy = 0: a = 1, every product 0 -- they
+        // pass through both phases as no-ops, so there is no per-step validity test.
+        const int steps4 = (len + 3) & ~3;
+        float4* hist4 = reinterpret_cast<float4*>(shist) + tid;          // [t][NT] float4 = the lane's four states
         // ---- phase A: forward through the chunk, parking h_{t-1} ------------------------------------
-        for (int t = 0; t < len; ++t) {
-            const float dl = sdl[r * TP + t], uu = su[r * TP + t];
-            const float dlu = dl * uu;
-            float yp = 0.f;
+        for (int t4 = 0; t4 < steps4; t4 += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(sdl + r * TP + t4);
+            const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + t4);
+            float4 B4[NS], C4[NS];
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                const int n = q + S * j;
-                shist[(t * NS + j) * NT + tid] = h[j];
-                const float a = ex2_approx(dl * Ap[j]);
-                h[j] = fmaf(a, h[j], dlu * sB[n * TP + t]);
-                if (HAS_Z) yp = fmaf(h[j], sC[n * TP + t], yp);
+                B4[j] = *reinterpret_cast<const float4*>(sB + (q + S * j) * TP + t4);
+                if (HAS_Z) C4[j] = *reinterpret_cast<const float4*>(sC + (q + S * j) * TP + t4);
             }
-            if (HAS_Z) {
-                yp += __shfl_xor_sync(0xffffffffu, yp, 1);
-                yp += __shfl_xor_sync(0xffffffffu, yp, 2);
-                if (q == 0) sy[r * TP + t] = fmaf(Dd, uu, yp);
+            const float dls[4] = {d4.x, d4.y, d4.z, d4.w}, uus[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const float dl = dls[s4], dlu = dl * uus[s4];
+                hist4[(t4 + s4) * NT] = make_float4(h[0], h[1], h[2], h[3]);
+                const float bb[4] = {s4 == 0 ? B4[0].x : s4 == 1 ? B4[0].y : s4 == 2 ? B4[0].z : B4[0].w,
+                                     s4 == 0 ? B4[1].x : s4 == 1 ? B4[1].y : s4 == 2 ? B4[1].z : B4[1].w,
+                                     s4 == 0 ? B4[2].x : s4 == 1 ? B4[2].y : s4 == 2 ? B4[2].z : B4[2].w,
+                                     s4 == 0 ? B4[3].x : s4 == 1 ? B4[3].y : s4 == 2 ? B4[3].z : B4[3].w};
+                float x[4], w[4];
+                mul2(x[0], x[1], dl, dl, Ap[0], Ap[1]); mul2(x[2], x[3], dl, dl, Ap[2], Ap[3]);
+                mul2(w[0], w[1], dlu, dlu, bb[0], bb[1]); mul2(w[2], w[3], dlu, dlu, bb[2], bb[3]);
+                const float a0 = ex2_approx(x[0]), a1 = ex2_approx(x[1]), a2 = ex2_approx(x[2]), a3 = ex2_approx(x[3]);
+                fma2(h[0], h[1], a0, a1, h[0], h[1], w[0], w[1]);
+                fma2(h[2], h[3], a2, a3, h[2], h[3], w[2], w[3]);
+                if (HAS_Z) {
+                    const float cc[4] = {s4 == 0 ? C4[0].x : s4 == 1 ? C4[0].y : s4 == 2 ? C4[0].z : C4[0].w,
+                                         s4 == 0 ? C4[1].x : s4 == 1 ? C4[1].y : s4 == 2 ? C4[1].z : C4[1].w,
+                                         s4 == 0 ? C4[2].x : s4 == 1 ? C4[2].y : s4 == 2 ? C4[2].z : C4[2].w,
+                                         s4 == 0 ? C4[3].x : s4 == 1 ? C4[3].y : s4 == 2 ? C4[3].z : C4[3].w};
+                    float yp = fmaf(h[0], cc[0], fmaf(h[1], cc[1], fmaf(h[2], cc[2], h[3] * cc[3])));
+                    yp += __shfl_xor_sync(0xffffffffu, yp, 1);
+                    yp += __shfl_xor_sync(0xffffffffu, yp, 2);
+                    if (q == 0) sy[r * TP + t4 + s4] = fmaf(Dd, uus[s4], yp);
+                }
             }
         }
         // ---- phase B: reverse recurrence ---------------------------------------------------------------
-        for (int t = len - 1; t >= 0; --t) {
-            const float dl = sdl[r * TP + t], uu = su[r * TP + t], dy = sdy[r * TP + t], sg = ssg[r * TP + t];
-            const float dlu = dl * uu;
-            float adu = 0.f, adl = 0.f, v[8];
+        // h holds h_t of the step being processed: the state phase A ended in, then the h_{t-1} each step loads.
+        for (int t4 = steps4 - 4; t4 >= 0; t4 -= 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(sdl + r * TP + t4);
+            const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + t4);
+            const float4 y4 = *reinterpret_cast<const float4*>(sdy + r * TP + t4);
+            const float4 g4 = *reinterpret_cast<const float4*>(ssg + r * TP + t4);
+            float4 B4[NS], C4[NS];
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                const int n = q + S * j;
-                const float hp = shist[(t * NS + j) * NT + tid];
-                const float Bt = sB[n * TP + t], Ct = sC[n * TP + t];
-                const float a = ex2_approx(dl * Ap[j]);
-                const float ht = fmaf(a, hp, dlu * Bt);
-                const float gt = fmaf(dy, Ct, gcar[j]);
-                const float hpa = hp * a;
-                v[j] = gt * dlu;                       // dB_n contribution of this row
-                v[NS + j] = dy * ht;                   // dC_n contribution of this row
-                adu = fmaf(gt, Bt, adu);
-                adl = fmaf(gt, fmaf(Bt, uu, hpa * Araw[j]), adl);
-                dA[j] = fmaf(gt * hpa, dl, dA[j]);
-                gcar[j] = a * gt;
+                B4[j] = *reinterpret_cast<const float4*>(sB + (q + S * j) * TP + t4);
+                C4[j] = *reinterpret_cast<const float4*>(sC + (q + S * j) * TP + t4);
             }
-            adu += __shfl_xor_sync(0xffffffffu, adu, 1); adu += __shfl_xor_sync(0xffffffffu, adu, 2);
-            adl += __shfl_xor_sync(0xffffffffu, adl, 1); adl += __shfl_xor_sync(0xffffffffu, adl, 2);
-            const float ddraw = adl * sg;
-            if (q == 0) {
-                sdy[r * TP + t] = fmaf(Dd, dy, dl * adu);          // du
-                sdl[r * TP + t] = ddraw;                           // d(delta raw)
-                dD_acc = fmaf(dy, uu, dD_acc);
-                dbias_acc += ddraw;
-            }
-            // sum the 8 values over the 8 rows of this warp (lanes with equal q): transposing reduction
+            const float dls[4] = {d4.x, d4.y, d4.z, d4.w}, uus[4] = {u4.x, u4.y, u4.z, u4.w};
+            const float dys[4] = {y4.x, y4.y, y4.z, y4.w}, sgs[4] = {g4.x, g4.y, g4.z, g4.w};
+            float duo[4], ddo[4];
 #pragma unroll
-            for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                const bool hi = (lane & off) != 0;
+            for (int s4 = 3; s4 >= 0; --s4) {
+                const int t = t4 + s4;
+                const float dl = dls[s4], uu = uus[s4], dy = dys[s4], sg = sgs[s4];
+                const float dlu = dl * uu;
+                const float4 hp4 = hist4[t * NT];
+                const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+                const float bb[4] = {s4 == 0 ? B4[0].x : s4 == 1 ? B4[0].y : s4 == 2 ? B4[0].z : B4[0].w,
+                                     s4 == 0 ? B4[1].x : s4 == 1 ? B4[1].y : s4 == 2 ? B4[1].z : B4[1].w,
+                                     s4 == 0 ? B4[2].x : s4 == 1 ? B4[2].y : s4 == 2 ? B4[2].z : B4[2].w,
+                                     s4 == 0 ? B4[3].x : s4 == 1 ? B4[3].y : s4 == 2 ? B4[3].z : B4[3].w};
+                const float cc[4] = {s4 == 0 ? C4[0].x : s4 == 1 ? C4[0].y : s4 == 2 ? C4[0].z : C4[0].w,
+                                     s4 == 0 ? C4[1].x : s4 == 1 ? C4[1].y : s4 == 2 ? C4[1].z : C4[1].w,
+                                     s4 == 0 ? C4[2].x : s4 == 1 ? C4[2].y : s4 == 2 ? C4[2].z : C4[2].w,
+                                     s4 == 0 ? C4[3].x : s4 == 1 ? C4[3].y : s4 == 2 ? C4[3].z : C4[3].w};
+                float x[4], gt[4], ga[4], tt[4], v[8];
+                mul2(x[0], x[1], dl, dl, Ap[0], Ap[1]); mul2(x[2], x[3], dl, dl, Ap[2], Ap[3]);
+                const float a0 = ex2_approx(x[0]), a1 = ex2_approx(x[1]), a2 = ex2_approx(x[2]), a3 = ex2_approx(x[3]);
+                fma2(gt[0], gt[1], dy, dy, cc[0], cc[1], gcar[0], gcar[1]);                 // g_t
+                fma2(gt[2], gt[3], dy, dy, cc[2], cc[3], gcar[2], gcar[3]);
+                mul2(ga[0], ga[1], a0, a1, gt[0], gt[1]); mul2(ga[2], ga[3], a2, a3, gt[2], gt[3]);   // a_t g_t: the carry
+                mul2(tt[0], tt[1], ga[0], ga[1], hp[0], hp[1]); mul2(tt[2], tt[3], ga[2], ga[3], hp[2], hp[3]);   // g h_{t-1} a
+                mul2(v[0], v[1], gt[0], gt[1], dlu, dlu); mul2(v[2], v[3], gt[2], gt[3], dlu, dlu);   // dB_n of this row
+                mul2(v[4], v[5], dy, dy, h[0], h[1]); mul2(v[6], v[7], dy, dy, h[2], h[3]);           // dC_n of this row
+                float adu0, adu1, adA0, adA1;
+                mul2(adu0, adu1, gt[0], gt[1], bb[0], bb[1]);
+                fma2(adu0, adu1, gt[2], gt[3], bb[2], bb[3], adu0, adu1);                             // sum_n g B
+                mul2(adA0, adA1, tt[0], tt[1], Araw[0], Araw[1]);
+                fma2(adA0, adA1, tt[2], tt[3], Araw[2], Araw[3], adA0, adA1);                         // sum_n g h a A
+                fma2(dA[0], dA[1], tt[0], tt[1], dl, dl, dA[0], dA[1]);
+                fma2(dA[2], dA[3], tt[2], tt[3], dl, dl, dA[2], dA[3]);
 #pragma unroll
-                for (int i = 0; i < half; ++i) {
-                    const float send = hi ? v[i] : v[i + half];
-                    const float keep = hi ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int j = 0; j < NS; ++j) { gcar[j] = ga[j]; h[j] = hp[j]; }
+                float adu = adu0 + adu1, adA = adA0 + adA1;
+                adu += __shfl_xor_sync(0xffffffffu, adu, 1); adu += __shfl_xor_sync(0xffffffffu, adu, 2);
+                adA += __shfl_xor_sync(0xffffffffu, adA, 1); adA += __shfl_xor_sync(0xffffffffu, adA, 2);
+                const float ddraw = fmaf(adu, uu, adA) * sg;       // d delta = sum_n g (B u + h_{t-1} a A_n), times d softplus
+                duo[s4] = fmaf(Dd, dy, dl * adu);
+                ddo[s4] = ddraw;
+                if (q == 0) {
+                    dD_acc = fmaf(dy, uu, dD_acc);
+                    dbias_acc += ddraw;
+                }
+                // sum the 8 values over the 8 rows of this warp (lanes with equal q): transposing reduction
+#pragma unroll
+                for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                    const bool hi = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < half; ++i) {
+                        const float send = hi ? v[i] : v[i + half];
+                        const float keep = hi ? v[i + half] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                {
+                    const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+                    const int j = idx & 3, n = q + S * j;
+                    swred[(warp * T + t) * 32 + (idx < 4 ? n : 16 + n)] = v[0];
                 }
             }
-            {
-                const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
-                const int j = idx & 3, n = q + S * j;
-                swred[(warp * T + t) * 32 + (idx < 4 ? n : 16 + n)] = v[0];
+            if (q == 0) {
+                *reinterpret_cast<float4*>(sdy + r * TP + t4) = make_float4(duo[0], duo[1], duo[2], duo[3]);   // du
+                *reinterpret_cast<float4*>(sdl + r * TP + t4) = make_float4(ddo[0], ddo[1], ddo[2], ddo[3]);   // d(delta raw)
             }
         }
         __syncthreads();

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--peak", type=float, default=6550.7)
+    ap.add_argument("--bwd", action="store_true", help="also time forward + backward through selective_scan_fn")
     args = ap.parse_args()
     dt = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -42,7 +43,29 @@ def main():
         es = u.element_size()
         nbytes = es * args.batch * L * (3 * KD + 2 * 4 * 16)
         gbs = nbytes / ms / 1e6
-        print(json.dumps(dict(shape=[args.batch, KD, L], dtype=args.dtype, ms=round(ms, 4), min_ms=round(times[0], 4),
+        fb = None
+        if args.bwd:
+            from medmamba_b200 import selective_scan_fn
+            leaves = [t.clone().requires_grad_(True) for t in (u, delta, g["A"], Bm, Cm, g["D"], g["delta_bias"])]
+            dout = torch.randn_like(u)
+            def run_fb():
+                for t in leaves:
+                    t.grad = None
+                out = selective_scan_fn(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], None, leaves[6], True)
+                out.backward(dout)
+            for _ in range(3):
+                run_fb()
+            torch.cuda.synchronize()
+            tb = []
+            for _ in range(args.iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run_fb(); e1.record()
+                torch.cuda.synchronize()
+                tb.append(e0.elapsed_time(e1))
+            tb.sort()
+            fb = round(tb[len(tb) // 2], 4)
+        print(json.dumps(dict(shape=[args.batch, KD, L], dtype=args.dtype, ms=round(ms, 4), min_ms=round(times[0], 4), fwd_bwd_ms=fb,
                               GBps=round(gbs, 1), frac=round(gbs / args.peak, 3),
                               state_updates_per_ns=round(args.batch * KD * L * 16 / ms / 1e6, 2))))
 
