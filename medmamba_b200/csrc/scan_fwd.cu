@@ -416,6 +416,11 @@ __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams
                 *reinterpret_cast<float4*>(su + r * TP + tt) = yo;
             }
         }
+        if (p.chunk_state && valid) {      // training: the state after every chunk (what mmb_scan_bwd recomputes from)
+            float* cs = p.chunk_state + (((int64_t)b * p.dim + d) * p.nchunks + c) * p.N;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) cs[n] = h[j]; }
+        }
         __syncthreads();
         // y of this chunk: shared -> global (coalesced), optional silu(z) gate
         for (int idx = tid; idx < RT * T4; idx += NT) {
@@ -456,7 +461,7 @@ static int launch_scan_fwd_async(const ScanFwdParams& p, cudaStream_t stream) {
 // The cp.async path takes any fp32 layout the operator accepts (unit stride along L for u / delta, any strides for
 // B / C): 16-byte pieces where rows are 16-byte aligned and L-contiguous, 4-byte pieces otherwise.
 static bool async_path_ok(ScanFwdParams& p, int io_dtype, int bc_dtype) {
-    if (io_dtype != MMB_F32 || bc_dtype != MMB_F32 || p.chunk_state) return false;
+    if (io_dtype != MMB_F32 || bc_dtype != MMB_F32) return false;
     if (getenv("MMB_SCAN_SYNC")) return false;
     const auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
     if (!al(p.u, 4) || !al(p.delta, 4) || !al(p.Bm, 4) || !al(p.Cm, 4)) return false;
@@ -552,6 +557,7 @@ extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, co
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (async_path_ok(p, io_dtype, bc_dtype)) {
         // chunk length: 16 steps for one lane per row (128 rows per CTA: two buffer sets of 46 KB, 4 CTAs per SM)
+        if (chunk_state) return launch_scan_fwd_async<4, 16>(p, st);      // the checkpoint geometry: nchunks set above
         const int Ta = S == 1 ? 16 : 32;
         p.nchunks = (seqlen + Ta - 1) / Ta;
         switch (S) {
