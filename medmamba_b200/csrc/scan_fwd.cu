@@ -251,6 +251,91 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src, int src_by
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// four consecutive elements of a shared-memory tile -> float4
+template <typename T> __device__ __forceinline__ float4 load4_smem(const T* p);
+template <> __device__ __forceinline__ float4 load4_smem<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4_smem<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 load4_smem<__half>(const __half* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// The recurrence over one staged chunk (fp32 tiles with a row pitch of T + 4 floats), four steps per iteration; y
+// overwrites u in place.  Shared by the fp32 and the 16-bit cp.async kernels.
+template <int S, int T>
+__device__ __forceinline__ void scan_chunk_steps(float* __restrict__ su, const float* __restrict__ sd, const float* __restrict__ sB,
+                                                 const float* __restrict__ sC, const int r, const int q, const int steps,
+                                                 const float (&Ap)[kMaxState / S], float (&h)[kMaxState / S], const float Dd) {
+    constexpr int NS = kMaxState / S, JB = NS < 8 ? NS : 8, TP = T + 4;
+    for (int tt = 0; tt < steps; tt += 4) {
+        const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + tt);
+        const float4 d4 = *reinterpret_cast<const float4*>(sd + r * TP + tt);
+        const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+        float du[4], y[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { du[s] = dl[s] * uu[s]; y[s] = 0.f; }
+        if constexpr (NS >= 2) {
+            // two states per packed FMUL2 / FFMA2 (one issue slot for two fp32 operations), two y accumulators
+            float y2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int jb = 0; jb < NS; jb += JB) {
+                float4 Bv[JB], Cv[JB];
+#pragma unroll
+                for (int j = 0; j < JB; ++j) {
+                    const int n = q + S * (jb + j);
+                    Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
+                    Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int j = 0; j < JB; j += 2) {
+                        const float b0 = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
+                        const float b1 = s == 0 ? Bv[j + 1].x : s == 1 ? Bv[j + 1].y : s == 2 ? Bv[j + 1].z : Bv[j + 1].w;
+                        const float c0 = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
+                        const float c1 = s == 0 ? Cv[j + 1].x : s == 1 ? Cv[j + 1].y : s == 2 ? Cv[j + 1].z : Cv[j + 1].w;
+                        float x0, x1, w0, w1;
+                        mul2(x0, x1, dl[s], dl[s], Ap[jb + j], Ap[jb + j + 1]);
+                        mul2(w0, w1, du[s], du[s], b0, b1);
+                        const float a0 = ex2_approx(x0), a1 = ex2_approx(x1);
+                        fma2(h[jb + j], h[jb + j + 1], a0, a1, h[jb + j], h[jb + j + 1], w0, w1);
+                        fma2(y[s], y2[s], h[jb + j], h[jb + j + 1], c0, c1, y[s], y2[s]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) y[s] += y2[s];
+        } else {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const float bb = sB[q * TP + tt + s], cc = sC[q * TP + tt + s];
+                const float a = ex2_approx(dl[s] * Ap[0]);
+                h[0] = fmaf(a, h[0], du[s] * bb);
+                y[s] = fmaf(h[0], cc, y[s]);
+            }
+        }
+#pragma unroll
+        for (int off = S / 2; off > 0; off >>= 1) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) y[s] += __shfl_xor_sync(0xffffffffu, y[s], off);
+        }
+        if (q == 0) {
+            float4 yo;
+            yo.x = fmaf(Dd, uu[0], y[0]); yo.y = fmaf(Dd, uu[1], y[1]);
+            yo.z = fmaf(Dd, uu[2], y[2]); yo.w = fmaf(Dd, uu[3], y[3]);
+            *reinterpret_cast<float4*>(su + r * TP + tt) = yo;
+        }
+    }
+}
+
 template <int S, int T>
 __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams p) {
     constexpr int NT = 128, RT = NT / S, NS = kMaxState / S, JB = NS < 8 ? NS : 8, TP = T + 4, T4 = T / 4;
@@ -355,67 +440,7 @@ __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams
             }
         }
         __syncthreads();
-        const int steps = (len + 3) & ~3;
-        for (int tt = 0; tt < steps; tt += 4) {
-            const float4 u4 = *reinterpret_cast<const float4*>(su + r * TP + tt);
-            const float4 d4 = *reinterpret_cast<const float4*>(sd + r * TP + tt);
-            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-            float du[4], y[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { du[s] = dl[s] * uu[s]; y[s] = 0.f; }
-            if constexpr (NS >= 2) {
-                // two states per packed FMUL2 / FFMA2 (one issue slot for two fp32 operations), two y accumulators
-                float y2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int jb = 0; jb < NS; jb += JB) {
-                    float4 Bv[JB], Cv[JB];
-#pragma unroll
-                    for (int j = 0; j < JB; ++j) {
-                        const int n = q + S * (jb + j);
-                        Bv[j] = *reinterpret_cast<const float4*>(sB + n * TP + tt);
-                        Cv[j] = *reinterpret_cast<const float4*>(sC + n * TP + tt);
-                    }
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-#pragma unroll
-                        for (int j = 0; j < JB; j += 2) {
-                            const float b0 = s == 0 ? Bv[j].x : s == 1 ? Bv[j].y : s == 2 ? Bv[j].z : Bv[j].w;
-                            const float b1 = s == 0 ? Bv[j + 1].x : s == 1 ? Bv[j + 1].y : s == 2 ? Bv[j + 1].z : Bv[j + 1].w;
-                            const float c0 = s == 0 ? Cv[j].x : s == 1 ? Cv[j].y : s == 2 ? Cv[j].z : Cv[j].w;
-                            const float c1 = s == 0 ? Cv[j + 1].x : s == 1 ? Cv[j + 1].y : s == 2 ? Cv[j + 1].z : Cv[j + 1].w;
-                            float x0, x1, w0, w1;
-                            mul2(x0, x1, dl[s], dl[s], Ap[jb + j], Ap[jb + j + 1]);
-                            mul2(w0, w1, du[s], du[s], b0, b1);
-                            const float a0 = ex2_approx(x0), a1 = ex2_approx(x1);
-                            fma2(h[jb + j], h[jb + j + 1], a0, a1, h[jb + j], h[jb + j + 1], w0, w1);
-                            fma2(y[s], y2[s], h[jb + j], h[jb + j + 1], c0, c1, y[s], y2[s]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) y[s] += y2[s];
-            } else {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const float bb = sB[q * TP + tt + s], cc = sC[q * TP + tt + s];
-                    const float a = ex2_approx(dl[s] * Ap[0]);
-                    h[0] = fmaf(a, h[0], du[s] * bb);
-                    y[s] = fmaf(h[0], cc, y[s]);
-                }
-            }
-#pragma unroll
-            for (int off = S / 2; off > 0; off >>= 1) {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) y[s] += __shfl_xor_sync(0xffffffffu, y[s], off);
-            }
-            if (q == 0) {
-                float4 yo;
-                yo.x = fmaf(Dd, uu[0], y[0]); yo.y = fmaf(Dd, uu[1], y[1]);
-                yo.z = fmaf(Dd, uu[2], y[2]); yo.w = fmaf(Dd, uu[3], y[3]);
-                *reinterpret_cast<float4*>(su + r * TP + tt) = yo;
-            }
-        }
+        scan_chunk_steps<S, T>(su, sd, sB, sC, r, q, (len + 3) & ~3, Ap, h, Dd);
         if (p.chunk_state && valid) {      // training: the state after every chunk (what mmb_scan_bwd recomputes from)
             float* cs = p.chunk_state + (((int64_t)b * p.dim + d) * p.nchunks + c) * p.N;
 #pragma unroll
@@ -442,6 +467,213 @@ __global__ void __launch_bounds__(128) scan_fwd_async_kernel(const ScanFwdParams
 #pragma unroll
         for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) ls[n] = h[j]; }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit I/O (bf16 / fp16 u, delta, z, out; B / C in the same type or fp32) on the cp.async path: the raw tiles of chunk
+// c + 1 travel into a second staging set while chunk c is computed; a conversion pass (where the fp32 kernel runs its
+// softplus pass) expands them into the fp32 tiles the recurrence reads.  Pieces of 16 bytes (8 elements) where rows are
+// 16-byte aligned (L % 8 == 0), of 4 bytes (2 elements) for even row strides.
+template <int S, int T, typename io_t, typename bc_t>
+__global__ void __launch_bounds__(128) scan_fwd_async16_kernel(const ScanFwdParams p) {
+    constexpr int NT = 128, RT = NT / S, NS = kMaxState / S, TP = T + 4, T4 = T / 4;
+    constexpr int F32 = (2 * RT + 2 * kMaxState) * TP;                  // floats: su, sd, sB, sC
+    constexpr int RAW_IO = 2 * RT * T;                                   // io_t elements per staging set: u, delta
+    constexpr int RAW_BC = 2 * kMaxState * T;                            // bc_t elements per staging set: B, C
+    constexpr int RAW_BYTES = RAW_IO * (int)sizeof(io_t) + RAW_BC * (int)sizeof(bc_t);
+    constexpr int EB = 16 / (int)sizeof(bc_t);                           // B / C elements per 16-byte piece
+    extern __shared__ __align__(16) float smem[];
+    float* su = smem, *sd = su + RT * TP, *sB = sd + RT * TP, *sC = sB + kMaxState * TP;
+    uint8_t* raw0 = reinterpret_cast<uint8_t*>(smem + F32);
+    const int tid = threadIdx.x;
+    const int r = tid / S, q = tid % S;
+    const int b = blockIdx.z, g = blockIdx.y;
+    const int row0 = blockIdx.x * RT;
+    const int rows_here = min(RT, p.H - row0);
+    const bool valid = r < rows_here;
+    const int d = g * p.H + row0 + (valid ? r : 0);
+    const io_t* ub = reinterpret_cast<const io_t*>(p.u) + (int64_t)b * p.u_bs;
+    const io_t* db = reinterpret_cast<const io_t*>(p.delta) + (int64_t)b * p.d_bs;
+    const io_t* zb = p.z ? reinterpret_cast<const io_t*>(p.z) + (int64_t)b * p.z_bs : nullptr;
+    io_t* ob = reinterpret_cast<io_t*>(p.out) + (int64_t)b * p.o_bs;
+    const bc_t* Bb = reinterpret_cast<const bc_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
+    const bc_t* Cb = reinterpret_cast<const bc_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+    constexpr int VA = vec4_align<io_t>();
+    const bool vec_z = zb && ((reinterpret_cast<uintptr_t>(zb) % VA) == 0) && (p.z_ds % 4 == 0);
+    const bool vec_o = ((reinterpret_cast<uintptr_t>(ob) % VA) == 0) && (p.o_ds % 4 == 0);
+
+    float Ap[NS], h[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int n = q + S * j;
+        Ap[j] = (valid && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+        h[j] = 0.f;
+    }
+    const float Dd = (valid && p.Dv) ? p.Dv[d] : 0.f;
+    const bool vec_ud = (p.flags & 1) != 0, vec_bc = (p.flags & 2) != 0;
+
+    auto prefetch = [&](int c) {
+        io_t* ru = reinterpret_cast<io_t*>(raw0 + (c & 1) * RAW_BYTES);
+        io_t* rd = ru + RT * T;
+        bc_t* rB = reinterpret_cast<bc_t*>(rd + RT * T);
+        bc_t* rC = rB + kMaxState * T;
+        const int t0 = c * T, len = min(T, p.L - t0);
+        if (vec_ud) {
+            for (int idx = tid; idx < RT * (T / 8); idx += NT) {
+                const int rr = idx / (T / 8), tt = (idx % (T / 8)) * 8;
+                const bool rok = rr < rows_here;
+                const int64_t dd = g * p.H + row0 + (rok ? rr : 0);
+                const int nb = rok ? max(0, min(8, len - tt)) * 2 : 0;
+                const int ts = nb ? t0 + tt : 0;
+                cp_async16(ru + rr * T + tt, ub + dd * p.u_ds + ts, nb);
+                cp_async16(rd + rr * T + tt, db + dd * p.d_ds + ts, nb);
+            }
+        } else {
+            for (int idx = tid; idx < RT * (T / 2); idx += NT) {
+                const int rr = idx / (T / 2), tt = (idx % (T / 2)) * 2;
+                const bool rok = rr < rows_here;
+                const int64_t dd = g * p.H + row0 + (rok ? rr : 0);
+                const int nb = rok ? max(0, min(2, len - tt)) * 2 : 0;
+                const int ts = nb ? t0 + tt : 0;
+                cp_async4(ru + rr * T + tt, ub + dd * p.u_ds + ts, nb);
+                cp_async4(rd + rr * T + tt, db + dd * p.d_ds + ts, nb);
+            }
+        }
+        if (vec_bc) {
+            for (int idx = tid; idx < kMaxState * (T / EB); idx += NT) {
+                const int n = idx / (T / EB), tt = (idx % (T / EB)) * EB;
+                const int nb = n < p.N ? max(0, min(EB, len - tt)) * (int)sizeof(bc_t) : 0;
+                const int ts = nb ? t0 + tt : 0;
+                const int nn = n < p.N ? n : 0;
+                cp_async16(rB + n * T + tt, Bb + (int64_t)nn * p.B_ns + ts, nb);
+                cp_async16(rC + n * T + tt, Cb + (int64_t)nn * p.C_ns + ts, nb);
+            }
+        } else {
+            // 4-byte pieces: one fp32 element with any strides, or two 16-bit elements along L
+            constexpr int E4 = 4 / (int)sizeof(bc_t);
+            const bool n_fast = E4 == 1 && p.B_ns == 1 && p.B_ls != 1;
+            for (int idx = tid; idx < kMaxState * (T / E4); idx += NT) {
+                const int n = n_fast ? idx % kMaxState : idx / (T / E4);
+                const int tt = (n_fast ? idx / kMaxState : idx % (T / E4)) * E4;
+                const bool ok = n < p.N && tt < len;
+                const int nb = ok ? max(0, min(E4, len - tt)) * (int)sizeof(bc_t) : 0;
+                const int64_t off_b = ok ? (int64_t)n * p.B_ns + (int64_t)(t0 + tt) * p.B_ls : 0;
+                const int64_t off_c = ok ? (int64_t)n * p.C_ns + (int64_t)(t0 + tt) * p.C_ls : 0;
+                cp_async4(rB + n * T + tt, Bb + off_b, nb);
+                cp_async4(rC + n * T + tt, Cb + off_c, nb);
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(0);
+    for (int c = 0; c < p.nchunks; ++c) {
+        const io_t* ru = reinterpret_cast<const io_t*>(raw0 + (c & 1) * RAW_BYTES);
+        const io_t* rd = ru + RT * T;
+        const bc_t* rB = reinterpret_cast<const bc_t*>(rd + RT * T);
+        const bc_t* rC = rB + kMaxState * T;
+        const int t0 = c * T, len = min(T, p.L - t0);
+        if (c + 1 < p.nchunks) { prefetch(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        // expand the raw tiles: u as is; delta + bias, softplus, 0 beyond the sequence (a = 1, b = 0: state untouched)
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            float4 uv = make_float4(0.f, 0.f, 0.f, 0.f), dv = uv;
+            if (rr < rows_here) {
+                uv = load4_smem<io_t>(ru + rr * T + tt);
+                dv = load4_smem<io_t>(rd + rr * T + tt);
+                const float bs = p.bias ? p.bias[g * p.H + row0 + rr] : 0.f;
+                dv.x += bs; dv.y += bs; dv.z += bs; dv.w += bs;
+                if (p.softplus) { dv.x = softplus_f(dv.x); dv.y = softplus_f(dv.y); dv.z = softplus_f(dv.z); dv.w = softplus_f(dv.w); }
+                if (tt + 0 >= len) dv.x = 0.f;
+                if (tt + 1 >= len) dv.y = 0.f;
+                if (tt + 2 >= len) dv.z = 0.f;
+                if (tt + 3 >= len) dv.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(su + rr * TP + tt) = uv;
+            *reinterpret_cast<float4*>(sd + rr * TP + tt) = dv;
+        }
+        for (int idx = tid; idx < kMaxState * T4; idx += NT) {
+            const int n = idx / T4, tt = (idx % T4) * 4;
+            *reinterpret_cast<float4*>(sB + n * TP + tt) = load4_smem<bc_t>(rB + n * T + tt);
+            *reinterpret_cast<float4*>(sC + n * TP + tt) = load4_smem<bc_t>(rC + n * T + tt);
+        }
+        __syncthreads();
+        scan_chunk_steps<S, T>(su, sd, sB, sC, r, q, (len + 3) & ~3, Ap, h, Dd);
+        if (p.chunk_state && valid) {
+            float* cs = p.chunk_state + (((int64_t)b * p.dim + d) * p.nchunks + c) * p.N;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) cs[n] = h[j]; }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < RT * T4; idx += NT) {
+            const int rr = idx / T4, tt = (idx % T4) * 4;
+            if (rr < rows_here && tt < len) {
+                const int64_t dd = g * p.H + row0 + rr;
+                float4 y = *reinterpret_cast<const float4*>(su + rr * TP + tt);
+                if (zb) {
+                    const float4 zz = load_row4<io_t>(zb + dd * p.z_ds + t0, tt, len, vec_z);
+                    y.x *= silu_f(zz.x); y.y *= silu_f(zz.y); y.z *= silu_f(zz.z); y.w *= silu_f(zz.w);
+                }
+                store_row4<io_t>(ob + dd * p.o_ds + t0, tt, len, vec_o, y);
+            }
+        }
+        __syncthreads();      // su / sd are rewritten by the next chunk's expansion; its raw set by the prefetch of c + 2
+    }
+    if (p.last_state && valid) {
+        float* ls = p.last_state + ((int64_t)b * p.dim + d) * p.N;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { const int n = q + S * j; if (n < p.N) ls[n] = h[j]; }
+    }
+}
+
+template <int S, int T, typename io_t, typename bc_t>
+static int launch_scan_fwd_async16(const ScanFwdParams& p, cudaStream_t stream) {
+    constexpr size_t smem = sizeof(float) * (size_t)(2 * (128 / S) + 2 * kMaxState) * (T + 4) +
+                            2 * ((size_t)2 * (128 / S) * T * sizeof(io_t) + (size_t)2 * kMaxState * T * sizeof(bc_t));
+    auto kern = scan_fwd_async16_kernel<S, T, io_t, bc_t>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    const int RT = 128 / S;
+    dim3 grid((p.H + RT - 1) / RT, p.G, p.batch);
+    kern<<<grid, 128, smem, stream>>>(p);
+    return launch_status();
+}
+
+template <typename io_t, typename bc_t>
+static int dispatch_async16(const ScanFwdParams& p, int S, cudaStream_t st) {
+    switch (S) {
+        case 0: return launch_scan_fwd_async16<4, 16, io_t, bc_t>(p, st);      // checkpoint geometry
+        case 1: return launch_scan_fwd_async16<1, 16, io_t, bc_t>(p, st);
+        case 2: return launch_scan_fwd_async16<2, 32, io_t, bc_t>(p, st);
+        case 4: return launch_scan_fwd_async16<4, 32, io_t, bc_t>(p, st);
+        case 8: return launch_scan_fwd_async16<8, 32, io_t, bc_t>(p, st);
+        default: return launch_scan_fwd_async16<16, 32, io_t, bc_t>(p, st);
+    }
+}
+
+// 16-bit u / delta rows with an even stride (4-byte pieces) or 16-byte aligned (8-element pieces); B / C fp32 in any
+// layout the fp32 path takes, or 16-bit and contiguous along L with the same alignment rules.
+static bool async16_path_ok(ScanFwdParams& p, int io_dtype, int bc_dtype) {
+    if ((io_dtype != MMB_BF16 && io_dtype != MMB_F16) || (bc_dtype != MMB_F32 && bc_dtype != io_dtype)) return false;
+    if (getenv("MMB_SCAN_SYNC")) return false;
+    const auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
+    if (!al(p.u, 4) || !al(p.delta, 4) || p.u_ds % 2 || p.u_bs % 2 || p.d_ds % 2 || p.d_bs % 2) return false;
+    p.flags = 0;
+    if (al(p.u, 16) && al(p.delta, 16) && p.u_ds % 8 == 0 && p.u_bs % 8 == 0 && p.d_ds % 8 == 0 && p.d_bs % 8 == 0) p.flags |= 1;
+    if (bc_dtype == MMB_F32) {
+        if (!al(p.Bm, 4) || !al(p.Cm, 4)) return false;
+        if (al(p.Bm, 16) && al(p.Cm, 16) && p.B_ls == 1 && p.C_ls == 1 && p.B_ns % 4 == 0 && p.C_ns % 4 == 0 && p.B_bs % 4 == 0 &&
+            p.C_bs % 4 == 0 && p.B_gs % 4 == 0 && p.C_gs % 4 == 0) p.flags |= 2;
+    } else {
+        if (p.B_ls != 1 || p.C_ls != 1 || !al(p.Bm, 4) || !al(p.Cm, 4)) return false;
+        if (p.B_ns % 2 || p.C_ns % 2 || p.B_bs % 2 || p.C_bs % 2 || p.B_gs % 2 || p.C_gs % 2) return false;
+        if (al(p.Bm, 16) && al(p.Cm, 16) && p.B_ns % 8 == 0 && p.C_ns % 8 == 0 && p.B_bs % 8 == 0 && p.C_bs % 8 == 0 &&
+            p.B_gs % 8 == 0 && p.C_gs % 8 == 0) p.flags |= 2;
+    }
+    return true;
 }
 
 template <int S, int T>
@@ -567,6 +799,14 @@ extern "C" int mmb_scan_fwd(const void* u, const void* delta, const float* A, co
             case 8: return launch_scan_fwd_async<8, 32>(p, st);
             default: return launch_scan_fwd_async<16, 32>(p, st);
         }
+    }
+    if (async16_path_ok(p, io_dtype, bc_dtype)) {
+        const int Ta = (S == 0 || S == 1) ? 16 : 32;
+        p.nchunks = (seqlen + Ta - 1) / Ta;
+        if (io_dtype == MMB_BF16)
+            return bc_dtype == MMB_F32 ? dispatch_async16<__nv_bfloat16, float>(p, S, st)
+                                       : dispatch_async16<__nv_bfloat16, __nv_bfloat16>(p, S, st);
+        return bc_dtype == MMB_F32 ? dispatch_async16<__half, float>(p, S, st) : dispatch_async16<__half, __half>(p, S, st);
     }
     switch (io_dtype) {
         case MMB_F32: return dispatch_bc<float>(p, io_dtype, bc_dtype, S, st);
