@@ -197,6 +197,36 @@ def test_fused_backward_deterministic_and_bf16():
         assert err < 5e-2, err
 
 
+def test_training_side_stream_is_bit_identical(monkeypatch):
+    """The CNN branch of every block runs on a side stream in training (forward, and through autograd backward).  Three
+    steps with the side stream give the logits and every gradient of the single-stream run bit for bit: the fork / join
+    and the caching allocator's cross-stream reuse leave no race."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    x = torch.randn(8, 3, 96, 96, device="cuda")
+    y = torch.randint(0, 5, (8,), device="cuda")
+
+    def run(overlap):
+        monkeypatch.setenv("MMB_TRAIN_BRANCH_OVERLAP", overlap)
+        torch.manual_seed(1)
+        net = mm.VSSM(depths=[2, 2, 2, 2], dims=[32, 64, 128, 256], num_classes=5).cuda().train()
+        out = []
+        for _ in range(3):
+            net.zero_grad(set_to_none=True)
+            torch.manual_seed(2)                    # DropPath draws
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = net(x)
+            torch.nn.functional.cross_entropy(logits.float(), y).backward()
+            torch.cuda.synchronize()
+            out.append([logits.detach().clone()] + [p.grad.clone() for p in net.parameters()])
+        return out
+
+    one, two = run("0"), run("1")
+    for a, b in zip(one, two):
+        assert len(a) == len(b) and all(torch.equal(u, v) for u, v in zip(a, b))
+    assert all(torch.equal(u, v) for u, v in zip(two[0], two[2])), "side-stream run differs from step to step"
+
+
 @pytest.mark.parametrize("B,H,W,C,strided,bf16_out", [(2, 5, 7, 48, True, True), (1, 3, 3, 96, False, False),
                                                       (2, 14, 14, 384, True, True), (3, 4, 4, 512, False, False),
                                                       (2, 6, 6, 16, True, False)])
