@@ -19,5 +19,5 @@ for k, v in (d.get('configs') or {}).items():
         print(k, v['ms_per_step'], 'ms', v['value'], 'img/s', [(s['stage'], s['avg_ms'], s['alu']['frac']) for s in v['roofline_stages']])
     else:
         for r in v:
-            print('  scan', r['dtype'], r.get('bc_layout', ''), r['KD'], r['L'], 'fwd', r['fwd']['ms'], r['fwd']['hbm_frac'], 'fwd+bwd', r['fwd_bwd']['ms'], r['fwd_bwd']['hbm_frac'])
+            print('  scan', r['dtype'], r.get('bc_layout', ''), 'b%d' % r.get('batch', 64), r['KD'], r['L'], 'fwd', r['fwd']['ms'], r['fwd']['hbm_frac'], 'fwd+bwd', r['fwd_bwd']['ms'], r['fwd_bwd']['hbm_frac'])
 print('cpu', d.get('cpu_baseline'))
