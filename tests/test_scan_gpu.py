@@ -113,6 +113,28 @@ def test_scan_fwd_bf16_io(KD, L, batch):
     assert rel_err(out.float().cpu(), want) < 1e-2
 
 
+@pytest.mark.parametrize("bc_same", [False, True])
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("L", [64, 200, 50, 37, 8, 1])
+def test_scan_fwd_16bit_io_paths(L, dtype, tol, bc_same):
+    """Every staging path of the 16-bit forward: 16-byte pieces (L % 8 == 0), 4-byte pieces (even L), the synchronous
+    kernel (odd L); B / C in fp32 or in the I/O dtype; with the silu(z) gate and the last state."""
+    from medmamba_b200 import selective_scan_fn
+    inp = make_scan_inputs("stress", 3, 40, L, seed=L, with_z=True)
+    q = lambda t: t.to(dtype).float()
+    inp_q = dict(inp, u=q(inp["u"]), delta=q(inp["delta"]), z=q(inp["z"]))
+    if bc_same:
+        inp_q.update(B=q(inp["B"]), C=q(inp["C"]))
+    g = _gpu(inp_q)
+    bc = (lambda t: t.to(dtype)) if bc_same else (lambda t: t)
+    out, last = selective_scan_fn(g["u"].to(dtype), g["delta"].to(dtype), g["A"], bc(g["B"]), bc(g["C"]), g["D"],
+                                  g["z"].to(dtype), g["delta_bias"], True, True)
+    assert out.dtype == dtype
+    want, want_last = cscan.scan_fwd(**inp_q, delta_softplus=True, precision="f64")
+    assert rel_err(out.float().cpu(), want) < tol
+    assert rel_err(last.float().cpu(), want_last) < 1e-4
+
+
 def test_scan_fwd_linearity_full_size():
     """Size-independent property at the BASELINE size: out is linear in u for fixed delta, B, C."""
     inp = _gpu(make_scan_inputs("stress", 64, 384, 3136, seed=1))
