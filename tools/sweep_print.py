@@ -1,6 +1,7 @@
 """Pretty-prints the JSON lines of tools/core_bench.py / core_bwd_bench.py sweeps."""
 import json, sys
-for l in sys.stdin:
+# a file name as the first argument, else standard input (never block on a terminal-less stdin by accident)
+for l in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin):
     try:
         d = json.loads(l)
     except Exception:
