@@ -380,7 +380,7 @@ class VSSLayer(nn.Module):
 
     def forward(self, x):
         for blk in self.blocks:
-            x = checkpoint.checkpoint(blk, x) if self.use_checkpoint else blk(x)
+            x = checkpoint.checkpoint(blk, x, use_reentrant=False) if self.use_checkpoint else blk(x)
         return x if self.downsample is None else self.downsample(x)
 
 

@@ -227,6 +227,25 @@ def test_training_side_stream_is_bit_identical(monkeypatch):
     assert all(torch.equal(u, v) for u, v in zip(two[0], two[2])), "side-stream run differs from step to step"
 
 
+def test_use_checkpoint_matches_plain_backward():
+    """VSSM(use_checkpoint=True) (MedMamba.py:359-422: torch.utils.checkpoint around every block) recomputes each block's
+    forward -- fused kernels, state checkpoints, side-stream fork and all -- inside backward: same logits and gradients."""
+    import medmamba_b200 as mm
+    cfg = dict(depths=[1, 2, 1, 1], dims=[32, 64, 128, 256], num_classes=5, drop_path_rate=0.0)
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 5, (4,), device="cuda")
+    res = []
+    for ckpt in (False, True):
+        torch.manual_seed(3)
+        net = mm.VSSM(use_checkpoint=ckpt, **cfg).cuda().train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = net(x)
+        torch.nn.functional.cross_entropy(logits.float(), y).backward()
+        res.append([logits.detach()] + [p.grad.clone() for p in net.parameters()])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("B,H,W,C,strided,bf16_out", [(2, 5, 7, 48, True, True), (1, 3, 3, 96, False, False),
                                                       (2, 14, 14, 384, True, True), (3, 4, 4, 512, False, False),
                                                       (2, 6, 6, 16, True, False)])
