@@ -5,8 +5,9 @@
 namespace mmb {
 
 constexpr int kPartBlocks = 592;     // CTAs of the LayerNorm-type reducing kernels = rows of their partial buffers (4 per SM)
-constexpr int kConvPartBlocks = 296; // the same for dwconv3x3_silu_bwd_ds (128 registers, 40 KB of partials per CTA: 2 per SM;
-                                     // 592 CTAs ran 2.4x slower)
+constexpr int kConvPartBlocks = 296; // the same for dwconv3x3_silu_bwd_ds (128 registers by __launch_bounds__(256, 2) -- left to
+                                     // itself ptxas took 157 and ONE CTA fitted an SM, ncu r2s3 -- 40 KB of partials per
+                                     // CTA: 2 per SM; 592 CTAs ran 2.4x slower)
 
 // Per-CTA partial of two per-channel sums (dgamma / dbeta): every lane holds the sums of channel slot (gl + G i) over
 // the tokens it saw.  Warps are added in fixed order through shared memory, then the 32 / G token sub-groups of a
@@ -232,7 +233,7 @@ layernorm_bwd_kernel(const x_t* __restrict__ x, const dy_t* __restrict__ dy, con
 // dxc (tokens, D) fp32, the four direction slices of the core backward's dudir (tokens, 4, D) fp32, and the x_proj
 // GEMM's input gradient dxe (tokens, D) in the activation dtype.
 template <typename in_t>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dwconv3x3_silu_bwd_ds_kernel(const in_t* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                              const float* __restrict__ dxc, const float* __restrict__ dudir, const in_t* __restrict__ dxe,
                              float* __restrict__ ds, float* __restrict__ part,
@@ -252,12 +253,14 @@ dwconv3x3_silu_bwd_ds_kernel(const in_t* __restrict__ x, const float* __restrict
     }
     float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias + c));
-    const int64_t pixels = (int64_t)B * H * W;
+    const int pixels = B * H * W;                 // < 2^31 (checked by the entry point): 32-bit index arithmetic
     if (active) {
-        for (int64_t pix = (int64_t)blockIdx.x * TY + ty; pix < pixels; pix += (int64_t)gridDim.x * TY) {
-            const int w = (int)(pix % W);
-            const int h = (int)((pix / W) % H);
-            const int b = (int)(pix / ((int64_t)W * H));
+        for (int pix32 = blockIdx.x * TY + ty; pix32 < pixels; pix32 += gridDim.x * TY) {
+            const int64_t pix = pix32;
+            const int row = pix32 / W;
+            const int w = pix32 - row * W;
+            const int b = row / H;
+            const int h = row - b * H;
             const in_t* xb = x + (int64_t)b * x_batch + c;
             float s[4] = {bs.x, bs.y, bs.z, bs.w};
             float xn[9][4];
@@ -415,6 +418,7 @@ extern "C" int mmb_dwconv3x3_silu_bwd_ds(const void* x, const float* weight, con
     if (!x || !weight || (!dxc && !dudir && !dxc_extra) || !ds || !dwb_part) return MMB_ERR_INVALID_ARG;
     if (batch < 0 || H <= 0 || W <= 0 || D <= 0) return MMB_ERR_INVALID_ARG;
     if (D % 4 != 0 || D / 4 > 256 || x_pixel_stride % 4 != 0 || x_batch_stride % 4 != 0) return MMB_ERR_UNSUPPORTED;
+    if ((int64_t)batch * H * W > 0x7ffffff0LL - (int64_t)kConvPartBlocks * 256) return MMB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(dxc) | reinterpret_cast<uintptr_t>(ds) | reinterpret_cast<uintptr_t>(bias) |
          reinterpret_cast<uintptr_t>(dudir) | reinterpret_cast<uintptr_t>(dxc_extra)) % 16 != 0)
         return MMB_ERR_UNSUPPORTED;
