@@ -100,6 +100,7 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         for (int it = 0; it < kBwdStages - 1 && it < NB; ++it) issue(it);
     }
     __syncthreads();
+    int itn = kBwdStages - 1 < NB ? kBwdStages - 1 : NB;          // next block to load (thread 0)
 
     const int cl = tid / S, q = tid % S;      // channel inside the tile; which 16/S states this lane owns
     const int col = lane / S;                 // channel inside the warp
@@ -139,10 +140,23 @@ ss2d_core_bwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
 
     for (int it = 0; it < NB; ++it) {
         const int s = it % kBwdStages, ph = (it / kBwdStages) & 1;
-        if (tid == 0 && it + kBwdStages - 1 < NB) {
-            const int itn = it + kBwdStages - 1;
-            if (it > 0) mbar_wait(&empty[itn % kBwdStages], ((it - 1) / kBwdStages) & 1);
-            issue(itn);
+        // refill: thread 0 tests whether the slot's previous block was released by every warp and blocks only if the
+        // block it is about to compute was never requested (see ss2d_core_fwd.cu: waiting here ties warp 0 to the
+        // slowest warp of the CTA at every block)
+        if (tid == 0) {
+            while (itn < NB && itn - it < kBwdStages) {
+                const int iprev = itn - kBwdStages;
+                if (iprev >= 0) {
+                    uint64_t* eb = &empty[itn % kBwdStages];
+                    const uint32_t par = (iprev / kBwdStages) & 1;
+                    if (!mbar_test_wait(eb, par)) {
+                        if (itn > it) break;
+                        mbar_wait(eb, par);
+                    }
+                }
+                issue(itn);
+                ++itn;
+            }
         }
         __syncwarp();
         const int jb = NB - 1 - it;

@@ -131,6 +131,7 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
         for (int jb = jb0; jb < jb0 + kCoreStages - 1 && jb < jb1; ++jb) issue(jb);
     }
     __syncthreads();
+    int jn = jb0 + kCoreStages - 1 < jb1 ? jb0 + kCoreStages - 1 : jb1;     // next stage to load (thread 0)
 
     const int t = warp * 32 + lane;
     const int cl = t / S, q = t % S;            // channel inside the tile, state split index
@@ -196,11 +197,24 @@ ss2d_core_fwd_kernel(const __grid_constant__ CUtensorMap tmx_row, const __grid_c
     for (int js = jb0; js < jb1; ++js) {
         const int jl = js - jb0;
         const int s = jl % kCoreStages, ph = (jl / kCoreStages) & 1;
-        // refill the ring slot stage js-1 has just left (inline producer: one thread)
-        if (tid == 0 && js + kCoreStages - 1 < jb1) {
-            const int jn = js + kCoreStages - 1;
-            if (jl > 0) mbar_wait(&empty[(jn - jb0) % kCoreStages], ((jl - 1) / kCoreStages) & 1);
-            issue(jn);
+        // Refill the ring (inline producer: one thread).  The slot of stage jn was last used by stage jn - kCoreStages and is
+        // free once every warp released that one.  Thread 0 only TESTS for it here and blocks only when the stage this warp
+        // is about to compute has not been requested yet: waiting would tie warp 0 to the slowest warp of the CTA at every
+        // block, and a refill that is one block late still has kCoreStages - 2 blocks of lead (-1 % at stage 1).
+        if (tid == 0) {
+            while (jn < jb1 && jn - js < kCoreStages) {
+                const int jprev = jn - kCoreStages;
+                if (jprev >= jb0) {
+                    uint64_t* eb = &empty[(jn - jb0) % kCoreStages];
+                    const uint32_t par = ((jprev - jb0) / kCoreStages) & 1;
+                    if (!mbar_test_wait(eb, par)) {
+                        if (jn > js) break;
+                        mbar_wait(eb, par);
+                    }
+                }
+                issue(jn);
+                ++jn;
+            }
         }
         __syncwarp();
         mbar_wait(&full[s], ph);
