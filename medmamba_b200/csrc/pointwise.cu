@@ -3,6 +3,8 @@
 //   (y0+y2+y1+y3) -> LayerNorm -> * SiLU(z)   replaces MedMamba.py:298-301 (3 adds, transpose copy, LN, gate)
 //   cat + channel_shuffle(2) + residual       replaces MedMamba.py:355-357 and :308-320
 // Each reads its inputs once with 128-bit loads and writes its output once.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -191,6 +193,113 @@ dwconv3x3_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, const float* _
                     ow[e] = *reinterpret_cast<const uint32_t*>(&pr);
                 }
                 *reinterpret_cast<uint4*>(out + (((int64_t)b * H + h) * W + wx) * D + c) = o;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two output rows per thread (bf16 in / bf16 out).  ncu of the bf16x8 kernel above (profiles/r2s3_dwconv_fwd_s1_metrics.txt):
+// 30.6 thread instructions per output, 45 % of them integer / logic -- the bf16 -> fp32 shifts of 18 neighbour vectors, their
+// clamped 64-bit addresses and three run-time divisions per thread -- at 54 % issue-slot utilisation: the kernel is bound by
+// instructions per output.  Here a thread owns 4 channels x 4 pixels x 2 rows: the two output rows share two of their three
+// input rows, so 24 neighbour vectors (4 rows x 6 columns) serve 32 outputs instead of 36 -- a third fewer loads, unpack shifts
+// and addresses per output; the index is decomposed with multiply-high by host-computed reciprocals.  Per output the taps are
+// accumulated in the order of the kernel above (tap row, then column, then tap column), so results are bit-identical to it.
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_silu_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt,
+                                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int D,
+                                int64_t x_pix, int64_t x_batch, uint32_t magic_c4, uint32_t magic_strips) {
+    constexpr int WS = 4, RS = 2;
+    extern __shared__ __align__(16) float swt[];        // [tap][D]
+    for (int i = threadIdx.x; i < D * 9; i += blockDim.x) swt[(i % 9) * D + i / 9] = __ldg(wgt + i);
+    __syncthreads();
+    const int C4 = D / 4;
+    const int strips = (W + WS - 1) / WS;
+    const uint32_t per_img = (uint32_t)((H + RS - 1) / RS) * strips * C4;
+    const int b = blockIdx.y;
+    const __nv_bfloat16* xi = x + (int64_t)b * x_batch;
+    __nv_bfloat16* oi = out + (int64_t)b * H * W * D;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
+        const uint32_t t = __umulhi(idx, magic_c4);
+        const int c = (int)(idx - t * (uint32_t)C4) * 4;
+        const uint32_t rp = __umulhi(t, magic_strips);
+        const int w0 = (int)(t - rp * (uint32_t)strips) * WS, h0 = (int)rp * RS;
+        float acc[RS][WS][4];
+        {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+            for (int r = 0; r < RS; ++r)
+#pragma unroll
+                for (int i = 0; i < WS; ++i) { acc[r][i][0] = b0.x; acc[r][i][1] = b0.y; acc[r][i][2] = b0.z; acc[r][i][3] = b0.w; }
+        }
+        // all (RS + 2) x (WS + 2) neighbour loads issued up front from clamped coordinates, masked afterwards
+        uint2 nb[RS + 2][WS + 2];
+        int coff[WS + 2];
+#pragma unroll
+        for (int j = 0; j < WS + 2; ++j) coff[j] = min(max(w0 + j - 1, 0), W - 1) * (int)x_pix;
+#pragma unroll
+        for (int ir = 0; ir < RS + 2; ++ir) {
+            const int hy = min(max(h0 + ir - 1, 0), H - 1);
+            const __nv_bfloat16* rowp = xi + (int64_t)hy * W * x_pix + c;
+#pragma unroll
+            for (int j = 0; j < WS + 2; ++j) nb[ir][j] = __ldg(reinterpret_cast<const uint2*>(rowp + coff[j]));
+        }
+        const bool interior = h0 >= 1 && h0 + RS < H && w0 >= 1 && w0 + WS < W;
+        auto taps = [&](auto interior_tag) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value;
+#pragma unroll
+            for (int ir = 0; ir < RS + 2; ++ir) {
+                const bool hok = INTERIOR || ((h0 + ir - 1 >= 0) && (h0 + ir - 1 < H));
+                float vv[WS + 2][4];
+#pragma unroll
+                for (int j = 0; j < WS + 2; ++j) {
+                    uint32_t lo = nb[ir][j].x, hi = nb[ir][j].y;
+                    if (!INTERIOR) {
+                        const bool ok = hok && (w0 + j - 1 >= 0) && (w0 + j - 1 < W);
+                        const uint32_t mk = ok ? 0xffffffffu : 0u;
+                        lo &= mk; hi &= mk;
+                    }
+                    vv[j][0] = __uint_as_float(lo << 16); vv[j][1] = __uint_as_float(lo & 0xffff0000u);
+                    vv[j][2] = __uint_as_float(hi << 16); vv[j][3] = __uint_as_float(hi & 0xffff0000u);
+                }
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const int dy = ir - r;                   // tap row through which input row ir reaches output row r
+                    if (dy < 0 || dy > 2) continue;
+                    float4 wk[3];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) wk[dx] = *reinterpret_cast<const float4*>(swt + (dy * 3 + dx) * D + c);
+#pragma unroll
+                    for (int j = 0; j < WS + 2; ++j) {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int i = j - dx;
+                            if (i >= 0 && i < WS) {
+                                fma2(acc[r][i][0], acc[r][i][1], wk[dx].x, wk[dx].y, vv[j][0], vv[j][1], acc[r][i][0], acc[r][i][1]);
+                                fma2(acc[r][i][2], acc[r][i][3], wk[dx].z, wk[dx].w, vv[j][2], vv[j][3], acc[r][i][2], acc[r][i][3]);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if (interior) taps(std::true_type{}); else taps(std::false_type{});
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int hh = h0 + r;
+#pragma unroll
+            for (int i = 0; i < WS; ++i) {
+                const int wx = w0 + i;
+                if (hh < H && wx < W) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(silu_f(acc[r][i][0]), silu_f(acc[r][i][1]));
+                    const __nv_bfloat162 p1 = __floats2bfloat162_rn(silu_f(acc[r][i][2]), silu_f(acc[r][i][3]));
+                    uint2 o;
+                    o.x = *reinterpret_cast<const uint32_t*>(&p0);
+                    o.y = *reinterpret_cast<const uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(oi + ((int64_t)hh * W + wx) * D + c) = o;
+                }
             }
         }
     }
@@ -495,6 +604,8 @@ shuffle_cat_residual_kernel(const TB* __restrict__ left, const TB* __restrict__ 
     }
 }
 
+constexpr int kDwconvRowsDefault = 1;     // MMB_DWCONV_ROWS: 1 = two output rows per thread
+
 static int grid_for(int64_t work_items, int threads) {
     int64_t blocks = (work_items + threads - 1) / threads;
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -531,6 +642,22 @@ extern "C" int mmb_dwconv3x3_silu_fwd(const void* x, const float* weight, const 
     if (in_dtype == MMB_BF16 && out_dtype == MMB_BF16 && D % 8 == 0 && x_pixel_stride % 8 == 0 && x_batch_stride % 8 == 0 &&
         reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
         (!bias || reinterpret_cast<uintptr_t>(bias) % 16 == 0)) {
+        const char* rows_env = getenv("MMB_DWCONV_ROWS");
+        const uint64_t per_img = (uint64_t)((H + 1) / 2) * ((W + WS - 1) / WS) * (D / 4);
+        if ((rows_env ? atoi(rows_env) != 0 : kDwconvRowsDefault) && batch <= 65535 && per_img * (D / 4) < (1ull << 31) &&
+            (int64_t)(W - 1) * x_pixel_stride < (1LL << 31)) {
+            // multiply-high reciprocals: exact for n * d < 2^32 (n < per_img)
+            const uint32_t c4 = (uint32_t)(D / 4), strips = (uint32_t)((W + WS - 1) / WS);
+            const uint32_t m_c4 = (uint32_t)(((1ull << 32) + c4 - 1) / c4), m_st = (uint32_t)(((1ull << 32) + strips - 1) / strips);
+            int gx = (int)((per_img + 255) / 256);
+            const int capx = (num_sms() * 16 + batch - 1) / batch;
+            if (gx > capx) gx = capx < 1 ? 1 : capx;
+            dim3 grid(gx, batch);
+            dwconv3x3_silu_bf16_rows_kernel<<<grid, 256, (size_t)D * 36, st>>>(
+                reinterpret_cast<const __nv_bfloat16*>(x), weight, bias, reinterpret_cast<__nv_bfloat16*>(out), H, W, D,
+                x_pixel_stride, x_batch_stride, m_c4, m_st);
+            return launch_status();
+        }
         const int64_t items8 = (int64_t)batch * H * ((W + WS - 1) / WS) * (D / 8);
         dwconv3x3_silu_bf16x8_kernel<WS><<<grid_for(items8, 256), 256, (size_t)D * 36, st>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), weight, bias, reinterpret_cast<__nv_bfloat16*>(out), batch, H, W, D,
