@@ -221,9 +221,9 @@ dwconv3x3_silu_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, const float
     const __nv_bfloat16* xi = x + (int64_t)b * x_batch;
     __nv_bfloat16* oi = out + (int64_t)b * H * W * D;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
-        const uint32_t t = __umulhi(idx, magic_c4);
+        const uint32_t t = C4 == 1 ? idx : __umulhi(idx, magic_c4);
         const int c = (int)(idx - t * (uint32_t)C4) * 4;
-        const uint32_t rp = __umulhi(t, magic_strips);
+        const uint32_t rp = strips == 1 ? t : __umulhi(t, magic_strips);     // 2^32 / 1 does not fit the 32-bit reciprocal
         const int w0 = (int)(t - rp * (uint32_t)strips) * WS, h0 = (int)rp * RS;
         float acc[RS][WS][4];
         {

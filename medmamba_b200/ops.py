@@ -6,7 +6,9 @@ the contract of each entry point and DESIGN.md for the data layout.  CUDA only -
 from __future__ import annotations
 
 import ctypes
+import contextlib
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -183,7 +185,7 @@ def ss2d_core(xc, proj, Wdt, dt_bias, A, Ds, d_state: int, dt_rank: int, save_st
     return (ydir, hsave) if save_states else ydir
 
 
-def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False, xc=None, Ds=None):
+def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False, xc=None, Ds=None, dsum=None):
     """ydir (B, H, W, 4, D) -> LayerNorm(sum of directions) * SiLU(z) with z a (B, H, W, D) view.  fp32 ydir holds the
     full directional outputs; bf16 ydir holds their state terms and needs ``xc`` (bf16) and ``Ds`` (4*D) for the skip
     term u * sum_k Ds_k, added in fp32."""
@@ -194,13 +196,15 @@ def outnorm_gate(ydir, z, gamma, beta, eps: float, want_merged: bool = False, xc
     merged = torch.empty((B, H, W, D), dtype=torch.float32, device=dev) if want_merged else None
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
-    dsum = None
     if ydir.dtype == torch.bfloat16:
         if xc is None or Ds is None or xc.dtype != torch.bfloat16 or not xc.is_contiguous():
             raise ValueError("outnorm_gate: bf16 direction slices need the contiguous bf16 xc and Ds they were split from")
-        dsum = Ds.detach().float().view(4, D).sum(0).contiguous()
+        if dsum is None:                      # (the inference path passes the cached sum)
+            dsum = Ds.detach().float().view(4, D).sum(0).contiguous()
     elif ydir.dtype != torch.float32:
         raise TypeError(f"outnorm_gate: ydir must be float32 or bfloat16, got {ydir.dtype}")
+    else:
+        dsum = None                           # fp32 slices carry the skip term themselves
     with torch.cuda.device(dev), timed_launch("outnorm_gate_fwd", f"B={B},L={H * W},D={D}"):
         st = lib().mmb_outnorm_gate_fwd(ptr(ydir), ptr(z), ptr(g), ptr(bt), ptr(out), ptr(merged),
                                         ptr(xc if dsum is not None else None), ptr(dsum), i64(B * H * W),
@@ -381,6 +385,36 @@ def pack_x_proj(x_proj_weight: torch.Tensor, d_state: int, dt_rank: int) -> torc
 
 
 # ------------------------------------------------------------------------ composed forward (inference)
+_derived_cache = {}
+
+
+def _derived_params(x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, d_state: int, dt_rank: int, bf16: bool):
+    """What the inference path derives from an SS2D module's parameters on every call -- the packed x_proj weight (in the
+    GEMM's dtype), A = -exp(A_logs) (MedMamba.py:269-270, the same torch ops, so the same bits) and fp32 contiguous views
+    of the rest -- cached per module: ~8 small launches per block and forward otherwise (a sixth of the launches of a
+    batch-8 forward).  The key follows in-place updates (`_version`: optimizer steps, load_state_dict) and rebinding
+    through `.data` / `.to()` (data_ptr, device); entries die with their parameter (weak reference)."""
+    params = (x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params) or os.environ.get("MMB_PARAM_CACHE", "1") == "0":
+        key = None
+    else:
+        key = (bf16, d_state, dt_rank) + tuple((p._version, p.data_ptr(), p.device, p.dtype) for p in params)
+        ent = _derived_cache.get(id(x_proj_weight))
+        if ent is not None and ent[0]() is x_proj_weight and ent[1] == key:
+            return ent[2]
+    with torch.no_grad() if key is not None else contextlib.nullcontext():
+        w_packed = pack_x_proj(x_proj_weight.float(), d_state, dt_rank)
+        out = (w_packed.to(torch.bfloat16) if bf16 else w_packed, dt_projs_weight.float().contiguous(),
+               dt_projs_bias.float().contiguous(), (-torch.exp(A_logs.float())).contiguous(), Ds.float().contiguous())
+        out = out + (out[4].view(4, -1).sum(0).contiguous(),)        # sum_k Ds_k: the skip term's factor in the bf16 layout
+    if key is not None:
+        if len(_derived_cache) > 256:
+            for k in [k for k, v in _derived_cache.items() if v[0]() is None]:
+                del _derived_cache[k]
+        _derived_cache[id(x_proj_weight)] = (weakref.ref(x_proj_weight), key, out)
+    return out
+
+
 def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, norm_w, norm_b,
                eps, d_state, dt_rank):
     """Everything between in_proj and out_proj of SS2D.forward (MedMamba.py:292-301).
@@ -388,19 +422,18 @@ def ss2d_inner(xz, conv_w, conv_b, x_proj_weight, dt_projs_weight, dt_projs_bias
     B, H, W, D2 = xz.shape
     D = D2 // 2
     x, z = xz[..., :D], xz[..., D:]
-    w_packed = pack_x_proj(x_proj_weight.float(), d_state, dt_rank)
-    if xz.dtype == torch.bfloat16 and D % 8 == 0:
+    bf16 = xz.dtype == torch.bfloat16 and D % 8 == 0
+    w_x, Wdt_c, b_c, A, D_c, dsum = _derived_params(x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, d_state, dt_rank, bf16)
+    if bf16:
         # autocast: bf16 activations, tensor-core x_proj with fp32 accumulate AND fp32 output
         xc = dwconv3x3_silu(x, conv_w, conv_b, out_dtype=torch.bfloat16)
-        proj = torch.mm(xc.view(-1, D), w_packed.to(torch.bfloat16).t(), out_dtype=torch.float32).view(B, H, W, 4, -1)
+        proj = torch.mm(xc.view(-1, D), w_x.t(), out_dtype=torch.float32).view(B, H, W, 4, -1)
     else:
         xc = dwconv3x3_silu(x, conv_w, conv_b)
         with torch.autocast("cuda", enabled=False):      # fp32 x_proj whatever the caller's autocast dtype is
-            proj = (xc.view(-1, D) @ w_packed.t()).view(B, H, W, 4, -1)
-    A = -torch.exp(A_logs.float())
-    ydir = ss2d_core(xc, proj, dt_projs_weight.float().contiguous(), dt_projs_bias.float().contiguous(),
-                     A.contiguous(), Ds.float().contiguous(), d_state, dt_rank)
-    return outnorm_gate(ydir, z, norm_w, norm_b, eps, xc=xc, Ds=Ds)
+            proj = (xc.view(-1, D) @ w_x.t()).view(B, H, W, 4, -1)
+    ydir = ss2d_core(xc, proj, Wdt_c, b_c, A, D_c, d_state, dt_rank)
+    return outnorm_gate(ydir, z, norm_w, norm_b, eps, xc=xc, Ds=D_c, dsum=dsum)
 
 
 def shuffle_cat_residual(left, ssm, inp):

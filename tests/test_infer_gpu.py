@@ -111,3 +111,64 @@ def test_branch_overlap_is_bitwise_neutral(monkeypatch):
         torch.cuda.synchronize()
         outs.setdefault(flag, []).append(y.float().cpu())
     assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][0], outs["1"][1])
+
+
+@pytest.mark.parametrize("amp", [None, torch.bfloat16])
+def test_derived_parameter_cache_follows_the_parameters(amp, monkeypatch):
+    """ops._derived_params caches what the inference path derives from an SS2D module's parameters (packed x_proj weight,
+    A = -exp(A_logs), sum_k Ds_k).  Every way a parameter can change -- an in-place update (optimizer step), load_state_dict,
+    rebinding `.data` -- must give the logits of an uncached forward, bit for bit."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.VSSM(depths=[1, 1], dims=[32, 64], num_classes=5).cuda().eval()
+    x = torch.randn(3, 3, 64, 64, device="cuda")
+
+    def run(cache):
+        monkeypatch.setenv("MMB_PARAM_CACHE", "1" if cache else "0")
+        with torch.no_grad(), torch.autocast("cuda", dtype=amp or torch.bfloat16, enabled=amp is not None):
+            return net(x).float().clone()
+
+    ss = [m for m in net.modules() if isinstance(m, mm.SS2D)]
+
+    def derived_are_current():
+        # the logits of this tiny net need not move under bf16 rounding, so the cached tensors themselves are checked too
+        monkeypatch.setenv("MMB_PARAM_CACHE", "1")
+        for m in ss:
+            with torch.no_grad():
+                w, Wdt, b, A, Dc, dsum = mm.ops._derived_params(m.x_proj_weight, m.dt_projs_weight, m.dt_projs_bias, m.A_logs,
+                                                               m.Ds, m.d_state, m.dt_rank, amp is not None)
+                wp = mm.ops.pack_x_proj(m.x_proj_weight.float(), m.d_state, m.dt_rank)
+                assert torch.equal(w, wp.to(torch.bfloat16) if amp is not None else wp)
+                assert torch.equal(Wdt, m.dt_projs_weight.float()) and torch.equal(b, m.dt_projs_bias.float())
+                assert torch.equal(A, -torch.exp(m.A_logs.float())) and torch.equal(Dc, m.Ds.float())
+                assert torch.equal(dsum, m.Ds.float().view(4, -1).sum(0))
+
+    first = run(True)
+    assert torch.equal(first, run(True)) and torch.equal(first, run(False))
+    derived_are_current()
+    with torch.no_grad():
+        ss[0].x_proj_weight.mul_(1.5)                          # in-place: _version changes
+        ss[1].A_logs.add_(0.25)
+        ss[0].Ds.mul_(-2.0)
+    second = run(True)
+    assert not torch.equal(first, second)
+    assert torch.equal(second, run(False))
+    derived_are_current()
+    with torch.no_grad():
+        ss[1].dt_projs_bias.data = ss[1].dt_projs_bias.data + 0.5      # rebinding: data_ptr changes
+    third = run(True)
+    assert torch.equal(third, run(False))
+    derived_are_current()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    for k in sd:
+        if k.endswith("A_logs") or k.endswith("x_proj_weight"):
+            sd[k] = sd[k] * 0.9
+    net.load_state_dict(sd)
+    fourth = run(True)
+    assert torch.equal(fourth, run(False))
+    derived_are_current()
+    # training mode / gradients wanted: nothing cached, gradients reach the parameters
+    net.train()
+    out = net(x)
+    out.sum().backward()
+    assert ss[0].x_proj_weight.grad is not None and ss[1].A_logs.grad is not None
