@@ -61,7 +61,8 @@ int mmb_scan_chunk_len(void);
  *   last_state       : NULL or (batch, dim, dstate) fp32 contiguous
  *   chunk_state      : NULL or (batch, dim, nchunks, dstate) fp32: state at the END of each chunk
  *                      of mmb_scan_chunk_len() steps (what the backward recomputes from)
- * dstate <= 16. */
+ * dstate <= 16 per launch: states are independent, so a caller with more runs groups of 16 over strided A / Bm / Cm views
+ * and adds the outputs (medmamba_b200/selective_scan_interface.py:_wide_state_scan). */
 int mmb_scan_fwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
                  const float* Dv, const void* z, const float* delta_bias, void* out,
                  float* last_state, float* chunk_state,

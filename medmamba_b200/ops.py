@@ -52,7 +52,8 @@ def fused_available() -> bool:
 def fused_supported(d_state: int, dt_rank: int, d_inner: int) -> bool:
     """Shape limits of the fused SS2D kernels: d_state <= 16, dt_rank <= 32, d_inner % 4 == 0.  Configurations the
     reference can construct outside them (VSSM(d_state=None, dims=[128, ...]) gives d_state 22) take the
-    reference-order path, whose scan still runs in mmb_scan_fwd when d_state <= 16 and raises otherwise."""
+    reference-order path; its scan runs in mmb_scan_fwd / mmb_scan_bwd, 16 states per launch (wider state spaces are split
+    into groups by selective_scan_fn)."""
     return d_state <= 16 and dt_rank <= 32 and d_inner % 4 == 0
 
 

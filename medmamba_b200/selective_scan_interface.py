@@ -48,7 +48,8 @@ def _check_shapes(u, delta, A, B, C, D, z, delta_bias):
         raise ValueError("complex A is not supported (MedMamba.py:28 asserts it away)")
     N = A.shape[1]
     if N > MAX_DSTATE:
-        raise ValueError(f"dstate {N} > {MAX_DSTATE} is not supported by the sm_100a kernels")
+        raise ValueError(f"dstate {N} > {MAX_DSTATE}: one launch of the sm_100a kernels holds at most {MAX_DSTATE} states per "
+                         f"row; selective_scan_fn splits wider state spaces into groups of {MAX_DSTATE}")
     for name, M in (("B", B), ("C", C)):
         if M.shape[0] != batch or M.shape[-2] != N or M.shape[-1] != L:
             raise ValueError(f"{name} {tuple(M.shape)} does not match (batch={batch}, ..., N={N}, L={L})")
@@ -205,6 +206,8 @@ class SelectiveScanFn(torch.autograd.Function):
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
     """See the module docstring; signature of mamba_ssm's ``selective_scan_fn`` (MedMamba.py:12)."""
+    if A.dim() == 2 and A.shape[1] > MAX_DSTATE:
+        return _wide_state_scan(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
     tensors = (u, delta, A, B, C, D, z, delta_bias)
     if not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)):
         # inference (also under no_grad with leaves that require grad: ctx.needs_input_grad does not see grad mode):
@@ -213,3 +216,33 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
                                     want_last_state=return_last_state, want_chunk_state=False)
         return (out, last) if return_last_state else out
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+def _wide_state_scan(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state):
+    """dstate > 16 (the reference's kernel takes up to 256: temp.py:27-36; VSSM(d_state=None, dims=[128, ...]) gives 22).
+    The states of a row never interact -- h_n follows its own recurrence and y = sum_n C_n h_n + D u (temp.py:111-131) --
+    so the state axis is cut into groups of MAX_DSTATE, every group runs through the kernels as its own scan (B / C as
+    strided views of the caller's tensors, D in the first group only) and the group outputs are added in fp32; the gate
+    SiLU(z) is applied to the sum.  Gradients compose through autograd: one SelectiveScanFn node per group.  A
+    compatibility path (ceil(N / 16) launches), not a tuned one."""
+    if B.dim() not in (3, 4) or C.dim() not in (3, 4):
+        raise ValueError("B and C must be (B, N, L) or (B, G, N, L); constant B/C are not on MedMamba's path")
+    N = A.shape[1]
+    if B.shape[-2] != N or C.shape[-2] != N:
+        raise ValueError(f"B {tuple(B.shape)} / C {tuple(C.shape)} do not match dstate {N}")
+    io = u.dtype
+    # 16-bit callers: the group outputs would each be rounded to 16 bits before the sum, so the groups run with fp32 rows
+    uf, df = u.float(), delta.float()
+    acc, lasts = None, []
+    for n0 in range(0, N, MAX_DSTATE):
+        n1 = min(n0 + MAX_DSTATE, N)
+        r = selective_scan_fn(uf, df, A[:, n0:n1], B[..., n0:n1, :], C[..., n0:n1, :], D if n0 == 0 else None, None,
+                              delta_bias, delta_softplus, return_last_state)
+        y = r[0] if return_last_state else r
+        acc = y if acc is None else acc + y
+        if return_last_state:
+            lasts.append(r[1])
+    if z is not None:
+        acc = acc * torch.nn.functional.silu(z.float())
+    out = acc.to(io)
+    return (out, torch.cat(lasts, dim=-1)) if return_last_state else out

@@ -145,3 +145,43 @@ def test_scan_fwd_linearity_full_size():
     lhs = f(inp["u"] + 2.0 * u2)
     rhs = f(inp["u"]) + 2.0 * f(u2)
     assert rel_err(lhs, rhs) < 1e-5
+
+
+@pytest.mark.parametrize("with_z", [False, True])
+@pytest.mark.parametrize("batch,KD,L,G,N", [(2, 24, 37, 4, 22), (1, 8, 130, 1, 17), (3, 12, 64, 2, 48), (1, 4, 9, 4, 256)])
+def test_scan_wide_state_forward(batch, KD, L, G, N, with_z):
+    """dstate > 16 (temp.py:27-36 allows up to 256): the interface runs groups of 16 states as separate launches and adds
+    their outputs; out, out - u*D and last_state against the fp64 oracle at the fp32 bar."""
+    inp = make_scan_inputs("stress", batch, KD, L, N=N, G=G, seed=N + L, with_z=with_z)
+    out, last = _run(inp, last=True)
+    want, want_last = selective_scan_ref(**inp, delta_softplus=True, return_last_state=True,
+                                         compute_dtype=torch.float64)
+    assert out.dtype == torch.float32 and last.shape == (batch, KD, N)
+    sc = max(1.0, want.abs().max().item())
+    assert_close(out.double().cpu() / sc, want / sc, 1e-4, 1e-5, "out")
+    assert_close(last.double().cpu() / sc, want_last.double() / sc, 1e-4, 1e-5, "last_state")
+    if not with_z:
+        uD = (inp["u"] * inp["D"][None, :, None]).double()
+        assert_close((out.double().cpu() - uD) / sc, (want - uD) / sc, 1e-4, 1e-5, "out - u*D")
+    out16 = _run(inp, dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and rel_err(out16.double().cpu(), want) < 1e-2
+
+
+def test_scan_wide_state_backward():
+    """Gradients of the 22-state scan (two launches, composed by autograd) against the analytic fp64 backward."""
+    from medmamba_b200 import selective_scan_fn
+    from oracle.selective_scan_ref import selective_scan_bwd_ref
+    batch, KD, L, N = 2, 16, 50, 22
+    inp = make_scan_inputs("stress", batch, KD, L, N=N, G=4, seed=5, with_z=True)
+    g = {k: (v.cuda().requires_grad_(True) if v is not None else None) for k, v in inp.items()}
+    out = selective_scan_fn(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["z"], g["delta_bias"], True)
+    torch.manual_seed(1)
+    dout = torch.randn(batch, KD, L)
+    out.backward(dout.cuda())
+    want = selective_scan_bwd_ref(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"],
+                                  inp["delta_bias"], True, dout)
+    for name in ["u", "delta", "A", "B", "C", "D", "z", "delta_bias"]:
+        w = want["d" + name]
+        got = g[name].grad.double().cpu()
+        sc = max(1.0, w.abs().max().item())
+        assert_close(got / sc, w.double().reshape(got.shape) / sc, 2e-3, 2e-4, "d" + name)

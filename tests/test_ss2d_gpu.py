@@ -395,14 +395,25 @@ def test_ss2d_core_rejects_half_precision_proj():
 
 def test_unsupported_state_size_takes_the_reference_order_path():
     """VSSM(d_state=None, dims=[128, ...]) gives d_state 22 (MedMamba.py:449): outside the fused kernel's limits, the
-    module must not select it (ops.fused_supported) -- the failure, if any, is the scan's clear ValueError."""
+    module must not select it (ops.fused_supported); the reference-order path runs it through selective_scan_fn, which
+    splits the 22 states into two launches.  Checked against the oracle's SS2D forward with the module's weights."""
     import medmamba_b200 as mm
     from medmamba_b200 import ops
+    from oracle import medmamba_ref
     assert not ops.fused_supported(22, 4, 128) and ops.fused_supported(16, 24, 768)
-    m = mm.SS2D(d_model=8, d_state=22).cuda().eval()
-    with pytest.raises(ValueError, match="dstate"):
-        with torch.no_grad():
-            m(torch.randn(1, 4, 4, 8, device="cuda"))
+    torch.manual_seed(3)
+    m = mm.SS2D(d_model=8, d_state=22).eval()
+    x = torch.randn(2, 5, 4, 8)
+    sd = {"m." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    want = medmamba_ref.ss2d_forward(sd, "m.", x)
+    m = m.cuda()
+    with torch.no_grad():
+        got = m(x.cuda())
+    assert_close(got.double().cpu(), want.double(), 1e-4, 1e-5, "SS2D d_state 22")
+    # gradients flow through both state groups
+    xg = x.cuda().requires_grad_(True)
+    m(xg).square().sum().backward()
+    assert torch.isfinite(xg.grad).all() and m.A_logs.grad.abs().sum(0)[16:].min() > 0
     with pytest.raises(ValueError):
         ops.pack_x_proj(torch.zeros(4, 1 + 44, 16, device="cuda"), 22, 1)
 
