@@ -228,6 +228,8 @@ def _wide_state_scan(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return
     if B.dim() not in (3, 4) or C.dim() not in (3, 4):
         raise ValueError("B and C must be (B, N, L) or (B, G, N, L); constant B/C are not on MedMamba's path")
     N = A.shape[1]
+    if N > 256:
+        raise ValueError(f"dstate {N} > 256 (the limit of the operator this replaces)")
     if B.shape[-2] != N or C.shape[-2] != N:
         raise ValueError(f"B {tuple(B.shape)} / C {tuple(C.shape)} do not match dstate {N}")
     io = u.dtype

@@ -93,8 +93,11 @@ def test_scan_fwd_empty_and_errors():
     assert out.shape == (0, 8, 5)
     with pytest.raises(ValueError):
         selective_scan_fn(z(1, 8, 5), z(1, 8, 4), -torch.ones(8, 16, device="cuda"), z(1, 4, 16, 5), z(1, 4, 16, 5))
-    with pytest.raises(ValueError):
-        selective_scan_fn(z(1, 8, 5), z(1, 8, 5), -torch.ones(8, 32, device="cuda"), z(1, 4, 32, 5), z(1, 4, 32, 5))
+    with pytest.raises(ValueError):          # dstate 32 runs (two groups of 16), but B / C must carry 32 states too
+        selective_scan_fn(z(1, 8, 5), z(1, 8, 5), -torch.ones(8, 32, device="cuda"), z(1, 4, 16, 5), z(1, 4, 32, 5))
+    with pytest.raises(ValueError):          # the reference operator's own limit (dstate <= 256)
+        selective_scan_fn(z(1, 8, 5), z(1, 8, 5), -torch.ones(8, 257, device="cuda"), z(1, 4, 257, 5), z(1, 4, 257, 5))
+    assert selective_scan_fn(z(1, 8, 5), z(1, 8, 5), -torch.ones(8, 32, device="cuda"), z(1, 4, 32, 5), z(1, 4, 32, 5)).shape == (1, 8, 5)
     with pytest.raises(RuntimeError):
         selective_scan_fn(torch.zeros(1, 8, 5), torch.zeros(1, 8, 5), -torch.ones(8, 16), torch.zeros(1, 4, 16, 5),
                           torch.zeros(1, 4, 16, 5))
