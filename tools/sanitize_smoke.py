@@ -1,4 +1,5 @@
-"""Small shapes through every hand-written kernel family, for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`."""
+"""Small shapes through every hand-written kernel family (development aid; written for `compute-sanitizer --tool memcheck`, which this
+pool does not allow any more -- it still runs as a plain smoke of the ragged / degenerate shapes)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -41,5 +42,15 @@ out = mm.selective_scan_fn(u, dl, A, xdbl[..., R:R + Nn].permute(0, 1, 3, 2), xd
 out.sum().backward()
 with torch.no_grad():
     mm.selective_scan_fn(u, dl, A, xdbl[..., R:R + Nn].permute(0, 1, 3, 2), xdbl[..., R + Nn:].permute(0, 1, 3, 2))
+# dstate 22: two launches over strided state slices, forward and backward
+N2 = 22
+A2 = -torch.rand(4 * 24, N2, device=dev, requires_grad=True)
+B2 = torch.randn(2, 4, N2, L, device=dev, requires_grad=True)
+C2 = torch.randn(2, 4, N2, L, device=dev)
+mm.selective_scan_fn(u, dl, A2, B2, C2, torch.ones(4 * 24, device=dev), dl, None, True).sum().backward()
+# dwconv rows kernel at one strip / one channel group (the reciprocal bypass)
+for (b, h, w, c) in ((1, 7, 3, 40), (2, 5, 9, 4), (1, 1, 1, 8)):
+    xx = torch.randn(b, h, w, c, device=dev).bfloat16()
+    ops.dwconv3x3_silu(xx, torch.randn(c, 1, 3, 3, device=dev), torch.randn(c, device=dev), out_dtype=torch.bfloat16)
 torch.cuda.synchronize()
 print("sanitize_smoke ok")
