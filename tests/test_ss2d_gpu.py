@@ -551,3 +551,42 @@ def test_core_is_linear_in_u_at_the_bench_shape():
     scale = want.abs().max().item()
     assert ((y3 - want).abs().max().item()) <= 2e-5 * scale
     assert torch.isfinite(y3).all()
+
+
+@pytest.mark.parametrize("B,Hi,Wi,depths,dims", [
+    (1, 32, 32, [1, 1], [16, 32]),                      # 8 x 8 tokens, one image
+    (3, 100, 60, [1, 1, 1], [16, 32, 64]),              # 25 x 15 tokens: both patch merges truncate an odd row / column
+    (2, 52, 76, [2, 2], [24, 48]),                      # 13 x 19 tokens, 12-channel SSM branch (d_inner 24)
+    (5, 224, 224, [1, 1, 1, 1], [16, 32, 64, 128]),     # the four-stage pyramid at the real resolution, odd batch
+])
+def test_vssm_odd_grids_vs_oracle(B, Hi, Wi, depths, dims):
+    """Whole-model forward on grids the headline shape never exercises (odd token counts, truncating patch merges,
+    narrow channel groups) against the oracle's VSSM forward with the same weights: fp32 (TF32 off) at 2e-4 of the
+    logit range with identical top-1, channels-last and inference_mode inputs, and the 16-bit autocast paths
+    (MedMamba.py:96-111, 475-492)."""
+    import medmamba_b200 as mm
+    torch.manual_seed(B * Hi + Wi)
+    net = mm.VSSM(depths=depths, dims=dims, num_classes=4).eval()
+    x = torch.randn(B, 3, Hi, Wi)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        want = medmamba_ref.vssm_forward(sd, x, depths=tuple(depths))
+    net = net.cuda()
+    rel = lambda a: ((a.double().cpu() - want.double()).abs().max() / want.double().abs().max()).item()
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            got = net(x.cuda())
+            got_cl = net(x.cuda().contiguous(memory_format=torch.channels_last))
+        with torch.inference_mode():
+            got_im = net(x.cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert rel(got) < 2e-4, rel(got)
+    assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+    assert torch.equal(got_im, got) and rel(got_cl) < 2e-4
+    # (north_star's 1e-2 bf16 bar is asserted on MedMamba-T itself above; these 16-channel toy pyramids sit at 3e-3 .. 1e-2)
+    for dt, bar in ((torch.float16, 5e-3), (torch.bfloat16, 2e-2)):
+        with torch.no_grad(), torch.autocast("cuda", dtype=dt):
+            assert rel(net(x.cuda()).float()) < bar, (dt, rel(net(x.cuda()).float()))
