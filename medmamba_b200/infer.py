@@ -24,6 +24,8 @@ class GraphedForward:
 
     def __init__(self, net: torch.nn.Module, static_input: torch.Tensor, autocast_dtype: Optional[torch.dtype], pool=None):
         self.net, self.x, self.autocast_dtype = net, static_input, autocast_dtype
+        self._weights = list(net.parameters()) + list(net.buffers())
+        self._sig = self._signature()
         warm = torch.cuda.Stream(static_input.device)
         warm.wait_stream(torch.cuda.current_stream(static_input.device))
         with torch.cuda.stream(warm):
@@ -41,6 +43,15 @@ class GraphedForward:
                 return self.net(self.x)
             with torch.autocast("cuda", dtype=self.autocast_dtype):
                 return self.net(self.x)
+
+    def _signature(self):
+        return (len(self._weights), sum(t._version for t in self._weights), sum(t.data_ptr() for t in self._weights))
+
+    def stale(self) -> bool:
+        """True when a parameter or buffer changed since the capture (optimizer step, load_state_dict, `.data` rebinding,
+        `.to()`).  The captured kernels read tensors derived from the weights at capture time (the BN-folded CNN branch,
+        ops._derived_params), so a replay would still compute with the old ones: the owner must capture again."""
+        return self._signature() != self._sig
 
     def pool(self):
         return self.graph.pool()
@@ -86,7 +97,7 @@ class InferencePipeline:
         if not self._use_graph(x):
             return self._forward(x)
         ent = self._graphs[slot]
-        if ent is None or ent[0] is not x:
+        if ent is None or ent[0] is not x or ent[1].stale():
             other = self._graphs[slot ^ 1]
             pool = other[1].pool() if other is not None else None       # the two slots replay one after the other
             ent = self._graphs[slot] = (x, GraphedForward(self.net, x, self.autocast_dtype, pool=pool))

@@ -48,6 +48,37 @@ def test_graphed_forward_replays_the_eager_forward(amp):
     assert all(torch.equal(p, q) for p, q in zip(a, b))
 
 
+def test_graphed_pipeline_follows_weight_updates():
+    """A captured graph computes with tensors derived from the weights at capture time (folded BN, -exp(A_logs), packed
+    x_proj).  After load_state_dict / an in-place update the pipeline must capture again: logits equal the eager ones."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.VSSM(depths=[1, 1], dims=[32, 64], num_classes=5).cuda().eval()
+    pipe = mm.InferencePipeline(net, autocast_dtype=None, cuda_graph=True)
+    batches = [torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(i)).pin_memory() for i in range(3)]
+
+    def eager():
+        with torch.no_grad():
+            return [net(b.cuda()).float().cpu() for b in batches]
+
+    first = list(pipe.stream(batches))
+    assert all(torch.equal(p, q) for p, q in zip(first, eager()))
+    sd = {k: (v * 1.25 if v.is_floating_point() else v.clone()) for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    second = list(pipe.stream(batches))
+    assert all(torch.equal(p, q) for p, q in zip(second, eager()))
+    assert not any(torch.equal(p, q) for p, q in zip(first, second))
+    with torch.no_grad():
+        net.head.weight.mul_(-1.0)
+    third = list(pipe.stream(batches))
+    assert all(torch.equal(p, q) for p, q in zip(third, eager()))
+    gf = pipe._graphs[0][1]
+    assert not gf.stale()
+    with torch.no_grad():
+        net.layers[0].blocks[0].self_attention.A_logs.add_(0.1)
+    assert gf.stale()
+
+
 def test_pipeline_rejects_cpu_module():
     import medmamba_b200 as mm
     with pytest.raises(RuntimeError):
