@@ -88,7 +88,7 @@ def _build_locked(verbose: bool) -> str:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
     tmp = LIB_PATH + ".tmp"
-    subprocess.check_call([_nvcc(), "-shared", "-o", tmp] + objs + ["-lcudart"])
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs + ["-lcudart"])
     os.replace(tmp, LIB_PATH)                        # never expose a half-written library
     with open(os.path.join(HERE, "_build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
