@@ -590,3 +590,17 @@ def test_vssm_odd_grids_vs_oracle(B, Hi, Wi, depths, dims):
     for dt, bar in ((torch.float16, 5e-3), (torch.bfloat16, 2e-2)):
         with torch.no_grad(), torch.autocast("cuda", dtype=dt):
             assert rel(net(x.cuda()).float()) < bar, (dt, rel(net(x.cuda()).float()))
+
+
+def test_vssm_t_batch_2048_matches_batch_1024():
+    """Element offsets beyond 2^31 (at stage 1 the direction slices of 2048 images hold 2.5 G elements): the logits of a
+    2048-image bf16 forward are, image by image, the bits of the 1024-image forward of the same images."""
+    import medmamba_b200 as mm
+    torch.manual_seed(0)
+    net = mm.medmamba_t(num_classes=6).cuda().eval()
+    x = torch.randn(1024, 3, 224, 224, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a = net(x).float()
+        y = net(torch.cat([x, x.flip(0)], 0)).float()
+    assert torch.isfinite(a).all()
+    assert torch.equal(y[:1024], a) and torch.equal(y[1024:], a.flip(0))
